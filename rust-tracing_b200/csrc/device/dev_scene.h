@@ -1,0 +1,65 @@
+// Device scene layout: one "threaded" op stream of float4 words.
+//
+// The reference walks Box<(Node,AABB)> trees recursively, always left child first
+// (bvh.rs:90-113), with trait-object leaves (hittable.rs). Here the whole hittable graph —
+// nested BVHs, lists, Translate/RotateY instances, media — is flattened at upload into a single
+// array of variable-length ops laid out in that same depth-first, left-first order. Every op that
+// can be culled carries a skip link (the word index just past its subtree), so traversal is a
+// stackless loop `i = hit_box ? i + size : skip` that visits nodes in exactly the reference's
+// order, which also preserves its tie rules on equal t (sphere: open interval, earlier wins;
+// quad / medium: closed interval, later wins — sphere.rs:78, quad.rs:115).
+//
+// Word 0 of every op: xyz = payload, w = header bits (kind | flags<<4 | aux<<8).
+// All ops are >= 2 words so the first two words can be fetched together.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../../include/rt_b200.h"
+
+namespace rtdev {
+
+enum OpKind : uint32_t {
+    OP_INNER = 0,        // w0 = {lo.xyz, hdr}  w1 = {hi.xyz, skip}                      size 2
+    OP_SPHERE = 1,       // w0 = {c.xyz, hdr}   w1 = {r, mat, prim_id, precise_idx}      size 2 (+1 if moving: w2 = {center_vec.xyz, 0})
+    OP_QUAD = 2,         // w0 = {n.xyz, hdr}   w1 = {A.xyz, a0} w2 = {B.xyz, b0} w3 = {d, mat, prim_id, 0}   size 4
+                         //   alpha = A.p + a0, beta = B.p + b0 with A = v x w, B = w x u (scalar triple product form of quad.rs:121-122)
+    OP_XFORM_ENTER = 3,  // w0 = {lo.xyz, hdr}  w1 = {hi.xyz, skip} w2 = {a.xyz, sin} w3 = {b.xyz, cos}       size 4
+                         //   local = R(x - a) + b, R = rotate-y (hittable.rs:164-168); skip = word after the matching exit
+    OP_XFORM_EXIT = 4,   // w0 = {0,0,0, hdr}   w1 = {0,0,0,0}                           size 2
+    OP_MEDIUM = 5,       // w0 = {lo.xyz, hdr}  w1 = {hi.xyz, skip} w2 = {neg_inv_density, mat, prim_id, bkind}
+                         // w3 = {bbegin, bend, 0, 0} (bkind 1: word range of the boundary program, which follows inline)
+                         //   bkind 0: boundary is a sphere: w3 = {c.xyz, r}, w4 = {center_vec.xyz, precise_idx}  (size 5)
+    OP_BOX = 6,          // cube list as one slab primitive: w0 = {min.xyz, hdr} w1 = {max.xyz, mat} w2 = {first_quad_prim_id,0,0,0}  size 3
+};
+
+constexpr uint32_t FLAG_MOVING = 1u;   // sphere has center_vec
+constexpr uint32_t FLAG_PRECISE = 2u;  // sphere test runs in f64 (huge radius; SURVEY.md §7 "hard parts")
+
+constexpr int MEDIUM_BOUNDARY_SPHERE = 0;
+constexpr int MEDIUM_BOUNDARY_PROGRAM = 1;
+
+inline uint32_t make_hdr(uint32_t kind, uint32_t flags = 0, uint32_t aux = 0) { return kind | (flags << 4) | (aux << 8); }
+
+struct F4 { float x, y, z, w; };
+struct D4 { double x, y, z, w; };
+
+// Output of compile_scene (host memory), uploaded verbatim.
+struct CompiledScene {
+    std::vector<F4> ops;         // the op stream; world program = [0, ops.size())
+    std::vector<F4> materials;   // 2 words each: {kind, tex, param, 0} {albedo.xyz, 0}
+    std::vector<F4> textures;    // 2 words each: {kind, a, b, scale} {color.xyz, 0}
+    std::vector<F4> perlin_vec;  // 256 per table: {ranvec.xyz, 0}
+    std::vector<uint8_t> perlin_perm;  // 768 per table: perm_x | perm_y | perm_z
+    std::vector<D4> precise;     // per precise sphere: {c.xyz, r} {center_vec.xyz, 0}
+    int n_perlin = 0;
+    // word index of the op that starts each BVH hittable (for rt_bvh_export)
+    std::vector<int32_t> bvh_hittable_ids;
+    std::vector<std::vector<int32_t>> bvh_preorder_objects;
+    float scene_scale = 1.0f;    // largest |coordinate| of finite geometry (parity tolerances)
+};
+
+// Returns 0 or a negative rt_status; message in *err.
+int compile_scene(const rt_scene_desc* desc, CompiledScene* out, const char** err);
+
+}  // namespace rtdev

@@ -1,0 +1,652 @@
+// Kernels + device half of the C ABI (include/rt_b200.h).
+//
+// K1 render_kernel   persistent megakernel: the parallel loop of renderer.rs:26-49. One warp owns a
+//                    pool of (8x4 pixel tile) x (sample chunk) paths at a time; a lane whose path ends
+//                    takes the next path of the pool in the same iteration (ballot/popc ranking), so
+//                    lanes never idle on finished paths. Radiance sums go to a float4 framebuffer with
+//                    one vector reduction per path.
+// K2 hit_kernel      Hittable::hit on a ray batch (parity).
+// K3 finalize_kernel color_to_rgb(sum/spp) (color.rs:12-19, renderer.rs:55-58).
+// K4 texture_kernel / get_ray_kernel (parity), expand_image_kernel (upload), fma_peak_kernel.
+#include "rt_kernels.cuh"
+
+#include "../host/host_common.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rtdev;
+using rt_host::fail;
+
+namespace {
+
+constexpr int kBlockThreads = 128;
+constexpr int kTileW = 8, kTileH = 4;
+constexpr int kMaxPerlinShared = 4;
+
+struct RenderParams {
+    DevScene scene;
+    DevCamera cam;
+    uint64_t seed;
+    int64_t sample_begin;
+    int sample_count;
+    int chunk;            // samples per pool
+    int tiles_x, tiles_y;
+    int n_chunks;
+    float4* sum;          // W*H float4
+    unsigned int* work_counter;
+    unsigned long long* stats;   // [0] paths, [1] segments
+};
+
+__device__ __forceinline__ void red_add_f4(float4* addr, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+__device__ __forceinline__ void stage_perlin(const DevScene& S, float4* sh_vec, uint8_t* sh_perm) {
+    const int n = min(S.n_perlin, kMaxPerlinShared);
+    for (int k = threadIdx.x; k < n * 256; k += blockDim.x) sh_vec[k] = S.perlin_vec[k];
+    for (int k = threadIdx.x; k < n * 768; k += blockDim.x) sh_perm[k] = S.perlin_perm[k];
+    __syncthreads();
+}
+
+extern __shared__ float4 dyn_smem[];
+
+__global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParams prm) {
+    float4* sh_vec = dyn_smem;
+    uint8_t* sh_perm = reinterpret_cast<uint8_t*>(dyn_smem + kMaxPerlinShared * 256);
+    stage_perlin(prm.scene, sh_vec, sh_perm);
+    PerlinShared P{sh_vec, sh_perm};
+    const DevScene& S = prm.scene;
+    const DevCamera& C = prm.cam;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned n_tiles = (unsigned)(prm.tiles_x * prm.tiles_y);
+    const unsigned n_items = n_tiles * (unsigned)prm.n_chunks;
+
+    // warp-uniform pool state
+    int pool_next = 0, pool_size = 0;
+    int tile_x0 = 0, tile_y0 = 0, tile_w = 1, tile_n = 1;
+    int64_t pool_sample0 = 0;
+    bool no_more = false;
+
+    // per-lane path state
+    bool active = false;
+    Ray ray;
+    float3 L, T;
+    int depth = 0, origin_op = -1, pix = 0;
+    uint4 key;
+    unsigned long long n_paths = 0, n_segments = 0;
+
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (need) {
+            if (pool_next >= pool_size && !no_more) {
+                unsigned item = 0;
+                if (lane == 0) item = atomicAdd(prm.work_counter, 1u);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= n_items) {
+                    no_more = true;
+                } else {
+                    const unsigned chunk_idx = item / n_tiles, tile = item % n_tiles;   // chunk-major: concurrent warps spread over tiles
+                    tile_x0 = (int)(tile % (unsigned)prm.tiles_x) * kTileW;
+                    tile_y0 = (int)(tile / (unsigned)prm.tiles_x) * kTileH;
+                    tile_w = min(kTileW, C.width - tile_x0);
+                    const int tile_h = min(kTileH, C.height - tile_y0);
+                    tile_n = tile_w * tile_h;
+                    const int s0 = (int)chunk_idx * prm.chunk;
+                    const int ns = min(prm.chunk, prm.sample_count - s0);
+                    pool_sample0 = prm.sample_begin + s0;
+                    pool_size = tile_n * ns;
+                    pool_next = 0;
+                }
+            }
+            if (!active) {
+                const int idx = pool_next + __popc(need & lt_mask);
+                if (idx < pool_size) {
+                    const int pv = idx % tile_n, sv = idx / tile_n;
+                    const int px = tile_x0 + pv % tile_w, py = tile_y0 + pv / tile_w;
+                    pix = py * C.width + px;                                         // renderer.rs:32-33
+                    key = path_key(prm.seed, (uint32_t)pix, (uint32_t)(pool_sample0 + sv));
+                    ray = camera_ray(C, px, py, key);
+                    L = f3(0.0f, 0.0f, 0.0f);
+                    T = f3(1.0f, 1.0f, 1.0f);
+                    depth = 0;
+                    origin_op = -1;
+                    active = true;
+                    ++n_paths;
+                }
+            }
+            pool_next = min(pool_size, pool_next + __popc(need));
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (no_more) break;
+            continue;
+        }
+        if (active) {
+            // one bounce of ray_color (renderer.rs:139-155), iteratively
+            ++n_segments;
+            Best best;
+            best.t = __int_as_float(0x7f800000); best.op = -1; best.xf = -1;
+            traverse<true>(S, 0, S.n_words, ray, 0.001f, best, origin_op, key, (uint32_t)depth);
+            bool alive;
+            if (best.op < 0) {
+                L = L + T * C.background;                                            // renderer.rs:152-153
+                alive = false;
+            } else {
+                HitRec h;
+                finalize_hit(S, ray, best, h);
+                const uint32_t kind = (uint32_t)fbits(__ldg(S.ops + best.op).w) & 15u;
+                alive = shade(S, P, ray, h, key, (uint32_t)depth, L, T);
+                origin_op = (kind == OP_MEDIUM) ? -1 : best.op;
+                ++depth;
+                if (depth >= C.max_depth) alive = false;                             // depth <= 0 returns black (:140-142)
+            }
+            if (!alive) {
+                red_add_f4(prm.sum + pix, L.x, L.y, L.z, 1.0f);                      // avg_color += new_color (:39)
+                active = false;
+            }
+        }
+    }
+    // stats: one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) {
+        n_paths += __shfl_down_sync(0xffffffffu, n_paths, off);
+        n_segments += __shfl_down_sync(0xffffffffu, n_segments, off);
+    }
+    if (lane == 0) {
+        atomicAdd(prm.stats + 0, n_paths);
+        atomicAdd(prm.stats + 1, n_segments);
+    }
+}
+
+struct DevRayIn { float ox, oy, oz, dx, dy, dz, time, pad; };
+struct DevHitOut { float t, px, py, pz, nx, ny, nz, u, v; int hit, front_face, prim, mat; };
+
+__global__ void hit_kernel(DevScene S, const DevRayIn* rays, int64_t n, float tmin, float tmax, uint64_t seed, DevHitOut* out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const DevRayIn r = rays[k];
+    Ray ray;
+    ray.o = f3(r.ox, r.oy, r.oz); ray.d = f3(r.dx, r.dy, r.dz); ray.time = r.time;
+    Best best;
+    best.t = tmax; best.op = -1; best.xf = -1;
+    const uint4 key = path_key(seed, (uint32_t)k, 0u);
+    traverse<true>(S, 0, S.n_words, ray, tmin, best, -1, key, 0u);
+    DevHitOut o;
+    memset(&o, 0, sizeof(o));
+    o.prim = -1; o.mat = -1;
+    if (best.op >= 0) {
+        HitRec h;
+        finalize_hit(S, ray, best, h);
+        if (h.uv_lazy) sphere_uv(h.sn, &h.u, &h.v);
+        o.hit = 1; o.t = h.t;
+        o.px = h.p.x; o.py = h.p.y; o.pz = h.p.z;
+        o.nx = h.normal.x; o.ny = h.normal.y; o.nz = h.normal.z;
+        o.u = h.u; o.v = h.v;
+        o.front_face = h.front_face ? 1 : 0;
+        o.prim = h.prim; o.mat = h.mat;
+    }
+    out[k] = o;
+}
+
+__global__ void texture_kernel(DevScene S, int tex, const float* uvp, int64_t n, float* rgb) {
+    float4* sh_vec = dyn_smem;
+    uint8_t* sh_perm = reinterpret_cast<uint8_t*>(dyn_smem + kMaxPerlinShared * 256);
+    stage_perlin(S, sh_vec, sh_perm);
+    PerlinShared P{sh_vec, sh_perm};
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    HitRec h;
+    h.u = uvp[k * 5]; h.v = uvp[k * 5 + 1];
+    h.p = f3(uvp[k * 5 + 2], uvp[k * 5 + 3], uvp[k * 5 + 4]);
+    h.uv_lazy = false;
+    const float3 c = texture_value(S, P, tex, h);
+    rgb[k * 3] = c.x; rgb[k * 3 + 1] = c.y; rgb[k * 3 + 2] = c.z;
+}
+
+__global__ void get_ray_kernel(DevCamera C, const int64_t* pixel, const int64_t* sample, int64_t n, uint64_t seed, DevRayIn* out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint4 key = path_key(seed, (uint32_t)pixel[k], (uint32_t)sample[k]);
+    const Ray r = camera_ray(C, (int)(pixel[k] % C.width), (int)(pixel[k] / C.width), key);
+    DevRayIn o;
+    o.ox = r.o.x; o.oy = r.o.y; o.oz = r.o.z; o.dx = r.d.x; o.dy = r.d.y; o.dz = r.d.z; o.time = r.time; o.pad = 0.0f;
+    out[k] = o;
+}
+
+// color_to_rgb(sum/spp): x^(1/2.2), clamp [0, 0.999], *256 -> u8; NaN -> 0 (Rust saturating cast)
+__global__ void finalize_kernel(const float4* sum, int64_t n, float inv_spp, int use_w, uint8_t* rgb) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 s = sum[k];
+    const float sc = use_w ? 1.0f / s.w : inv_spp;
+    const float c[3] = {s.x * sc, s.y * sc, s.z * sc};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float g = powf(c[j], 1.0f / 2.2f);
+        g = fminf(fmaxf(g, 0.0f), 0.999f);   // fmaxf(NaN, 0) = 0
+        rgb[k * 3 + j] = (uint8_t)(256.0f * g);
+    }
+}
+
+__global__ void expand_image_kernel(const uint8_t* rgb8, int64_t n, const float* lut, float4* out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[k] = make_float4(lut[rgb8[k * 3]], lut[rgb8[k * 3 + 1]], lut[rgb8[k * 3 + 2]], 0.0f);
+}
+
+__global__ void fma_peak_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+        a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? RT_ERR_NO_DEVICE
+                : e == cudaErrorMemoryAllocation                            ? RT_ERR_OUT_OF_MEMORY
+                                                                              : RT_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                            \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+size_t perlin_smem_bytes() { return (size_t)kMaxPerlinShared * (256 * sizeof(float4) + 768); }
+
+DevCamera make_dev_camera(const rt_camera_desc& c) {
+    DevCamera d;
+    d.width = (int)c.image_width;
+    d.height = (int)c.image_height;
+    d.max_depth = c.max_depth;
+    auto f = [](const double* p) { return make_float3((float)p[0], (float)p[1], (float)p[2]); };
+    d.background = f(c.background);
+    d.center = f(c.center);
+    d.rel00 = make_float3((float)(c.pixel00_loc[0] - c.center[0]), (float)(c.pixel00_loc[1] - c.center[1]),
+                          (float)(c.pixel00_loc[2] - c.center[2]));
+    d.du = f(c.pixel_delta_u);
+    d.dv = f(c.pixel_delta_v);
+    d.disk_u = f(c.defocus_disk_u);
+    d.disk_v = f(c.defocus_disk_v);
+    d.defocus = !(c.defocus_angle <= 0.0) ? 1 : 0;   // camera.rs:117
+    return d;
+}
+
+}  // namespace
+
+struct rt_context {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    size_t total_mem = 0;
+    int blocks_per_sm = 1;
+    unsigned int* d_counter = nullptr;
+    unsigned long long* d_stats = nullptr;
+    float4* d_fb = nullptr;
+    size_t fb_pixels = 0;
+    rt_render_stats last{};
+    uint64_t launches = 0;
+};
+
+struct rt_scene {
+    rt_context* ctx = nullptr;
+    DevScene dev{};
+    std::vector<void*> allocations;
+    CompiledScene compiled;
+};
+
+extern "C" {
+
+int rt_context_create(int device_id, rt_context** out) {
+    if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_context_create: out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(RT_ERR_NO_DEVICE, std::string("rt_context_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (device_id < 0 || device_id >= n) return fail(RT_ERR_OUT_OF_RANGE, "rt_context_create: device id out of range");
+    CU(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_id));
+    rt_context* c = new rt_context;
+    c->device = device_id;
+    c->sm_count = prop.multiProcessorCount;
+    c->total_mem = prop.totalGlobalMem;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
+    c->clock_khz = khz;
+    CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
+    int bps = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_kernel, kBlockThreads, perlin_smem_bytes()));
+    c->blocks_per_sm = bps > 0 ? bps : 1;
+    CU(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_stats, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_stats, 0, 2 * sizeof(unsigned long long)));
+    *out = c;
+    return RT_OK;
+}
+
+void rt_context_destroy(rt_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_counter);
+    cudaFree(c->d_stats);
+    cudaFree(c->d_fb);
+    delete c;
+}
+
+int rt_device_info(rt_context* c, int* sm_count, int* sm_clock_khz, size_t* total_mem) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_device_info: context is null");
+    if (sm_count) *sm_count = c->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = c->clock_khz;
+    if (total_mem) *total_mem = c->total_mem;
+    return RT_OK;
+}
+
+static int upload_vec(rt_scene* s, const void* src, size_t bytes, void** dst) {
+    *dst = nullptr;
+    const size_t alloc = bytes ? bytes : 16;
+    CU(cudaMalloc(dst, alloc));
+    s->allocations.push_back(*dst);
+    if (bytes) CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
+    if (!c || !desc || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: null argument");
+    CU(cudaSetDevice(c->device));
+    rt_scene* s = new rt_scene;
+    s->ctx = c;
+    const char* err = nullptr;
+    int rc = compile_scene(desc, &s->compiled, &err);
+    if (rc < 0) { delete s; return fail(rc, err ? err : "compile_scene failed"); }
+    if (s->compiled.n_perlin > kMaxPerlinShared) { delete s; return fail(RT_ERR_UNSUPPORTED, "more than 4 NoiseTexture tables in one scene"); }
+    const CompiledScene& cs = s->compiled;
+    void* p = nullptr;
+#define UP(vec, field, type)                                                                   \
+    rc = upload_vec(s, (vec).data(), (vec).size() * sizeof((vec)[0]), &p);                     \
+    if (rc < 0) { rt_scene_destroy(s); return rc; }                                            \
+    s->dev.field = static_cast<type>(p);
+    UP(cs.ops, ops, const float4*)
+    UP(cs.materials, mats, const float4*)
+    UP(cs.textures, texs, const float4*)
+    UP(cs.perlin_vec, perlin_vec, const float4*)
+    UP(cs.perlin_perm, perlin_perm, const uint8_t*)
+    UP(cs.precise, precise, const double4*)
+#undef UP
+    s->dev.n_words = (int)cs.ops.size();
+    s->dev.n_perlin = cs.n_perlin;
+    // images: upload RGB8, expand on the device to linear float4 through a 256-entry LUT computed in f64
+    std::vector<DevImage> imgs((size_t)desc->n_images);
+    if (desc->n_images > 0) {
+        float lut[256];
+        for (int k = 0; k < 256; ++k) lut[k] = (float)std::pow((double)k / 255.0, 2.2);   // color.rs:8-10,21-27
+        float* d_lut = nullptr;
+        rc = upload_vec(s, lut, sizeof(lut), (void**)&d_lut);
+        if (rc < 0) { rt_scene_destroy(s); return rc; }
+        for (int k = 0; k < desc->n_images; ++k) {
+            const rt_image_desc& im = desc->images[k];
+            if (im.width <= 0 || im.height <= 0 || !im.rgb8) { rt_scene_destroy(s); return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: empty image"); }
+            const int64_t n = (int64_t)im.width * im.height;
+            uint8_t* d_rgb = nullptr;
+            float4* d_tex = nullptr;
+            cudaError_t e = cudaMalloc(&d_rgb, (size_t)n * 3);
+            if (e != cudaSuccess) { rt_scene_destroy(s); return cuda_fail(e, "cudaMalloc(image rgb8)"); }
+            e = cudaMalloc(&d_tex, (size_t)n * sizeof(float4));
+            if (e != cudaSuccess) { cudaFree(d_rgb); rt_scene_destroy(s); return cuda_fail(e, "cudaMalloc(image texels)"); }
+            s->allocations.push_back(d_tex);
+            e = cudaMemcpy(d_rgb, im.rgb8, (size_t)n * 3, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                expand_image_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_rgb, n, d_lut, d_tex);
+                e = cudaDeviceSynchronize();
+            }
+            cudaFree(d_rgb);
+            if (e != cudaSuccess) { rt_scene_destroy(s); return cuda_fail(e, "image upload"); }
+            imgs[k].texels = d_tex;
+            imgs[k].width = im.width;
+            imgs[k].height = im.height;
+        }
+    }
+    rc = upload_vec(s, imgs.data(), imgs.size() * sizeof(DevImage), &p);
+    if (rc < 0) { rt_scene_destroy(s); return rc; }
+    s->dev.images = static_cast<const DevImage*>(p);
+    *out = s;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene* s) {
+    if (!s) return;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    for (void* p : s->allocations) cudaFree(p);
+    delete s;
+}
+
+int rt_render_accumulate(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
+                         int64_t sample_count, uint64_t seed, void* d_sum_rgba, void* stream_) {
+    if (!c || !s || !cam || !d_sum_rgba) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: null argument");
+    if (sample_count < 0 || sample_count > 0x7fffffff) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: bad sample_count");
+    if (cam->image_width <= 0 || cam->image_height <= 0 || cam->image_width * cam->image_height > 0x7fffffff)
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: bad image size");
+    if (sample_count == 0) return RT_OK;
+    if (cam->max_depth <= 0)   // ray_color returns black at depth <= 0 (renderer.rs:140-142); the CLI scenes never ask for it
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: max_depth must be positive");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RenderParams prm;
+    prm.scene = s->dev;
+    prm.cam = make_dev_camera(*cam);
+    prm.seed = seed;
+    prm.sample_begin = sample_begin;
+    prm.sample_count = (int)sample_count;
+    prm.tiles_x = (prm.cam.width + kTileW - 1) / kTileW;
+    prm.tiles_y = (prm.cam.height + kTileH - 1) / kTileH;
+    // pool = tile x chunk samples; keep enough items (>= 8 per resident warp) for the tail to stay short
+    const int64_t n_tiles = (int64_t)prm.tiles_x * prm.tiles_y;
+    const int64_t resident_warps = (int64_t)c->sm_count * c->blocks_per_sm * (kBlockThreads / 32);
+    int chunk = 32;
+    while (chunk > 1 && n_tiles * ((sample_count + chunk - 1) / chunk) < resident_warps * 8) chunk >>= 1;
+    prm.chunk = chunk;
+    prm.n_chunks = (int)((sample_count + chunk - 1) / chunk);
+    if ((uint64_t)n_tiles * (uint64_t)prm.n_chunks >= 0xffffffffull) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: too many work items; split the sample range");
+    prm.sum = static_cast<float4*>(d_sum_rgba);
+    prm.work_counter = c->d_counter;
+    prm.stats = c->d_stats;
+    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), stream));
+    CU(cudaMemsetAsync(c->d_stats, 0, 2 * sizeof(unsigned long long), stream));
+    const int grid = c->sm_count * c->blocks_per_sm;
+    render_kernel<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
+    CU(cudaGetLastError());
+    c->launches += 1;
+    return RT_OK;
+}
+
+int rt_render_get_stats(rt_context* c, rt_render_stats* out) {
+    if (!c || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_get_stats: null argument");
+    CU(cudaSetDevice(c->device));
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    out->paths = h[0];
+    out->segments = h[1];
+    out->kernel_launches = c->launches;
+    out->last_kernel_ms = 0.0f;
+    return RT_OK;
+}
+
+int rt_render(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin, int64_t sample_count,
+              uint64_t seed, float* host_sum_rgba) {
+    if (!c || !s || !cam || !host_sum_rgba) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: null argument");
+    if (cam->image_width <= 0 || cam->image_height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: bad image size");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)cam->image_width * (size_t)cam->image_height;
+    if (c->fb_pixels < n) {
+        cudaFree(c->d_fb);
+        c->d_fb = nullptr;
+        c->fb_pixels = 0;
+        CU(cudaMalloc(&c->d_fb, n * sizeof(float4)));
+        c->fb_pixels = n;
+    }
+    CU(cudaMemsetAsync(c->d_fb, 0, n * sizeof(float4), 0));
+    int rc = rt_render_accumulate(c, s, cam, sample_begin, sample_count, seed, c->d_fb, nullptr);
+    if (rc < 0) return rc;
+    CU(cudaMemcpy(host_sum_rgba, c->d_fb, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_finalize_rgb8(rt_context* c, const void* d_sum_rgba, int64_t n_pixels, double spp, uint8_t* host_rgb8) {
+    if (!c || !d_sum_rgba || !host_rgb8) return fail(RT_ERR_INVALID_ARGUMENT, "rt_finalize_rgb8: null argument");
+    if (n_pixels <= 0) return RT_OK;
+    CU(cudaSetDevice(c->device));
+    uint8_t* d_rgb = nullptr;
+    CU(cudaMalloc(&d_rgb, (size_t)n_pixels * 3));
+    finalize_kernel<<<(unsigned)((n_pixels + 255) / 256), 256>>>(static_cast<const float4*>(d_sum_rgba), n_pixels,
+                                                               spp > 0 ? (float)(1.0 / spp) : 0.0f, spp > 0 ? 0 : 1, d_rgb);
+    cudaError_t e = cudaMemcpy(host_rgb8, d_rgb, (size_t)n_pixels * 3, cudaMemcpyDeviceToHost);
+    cudaFree(d_rgb);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_finalize_rgb8");
+    return RT_OK;
+}
+
+int rt_hit_batch(rt_context* c, const rt_scene* s, const rt_ray_desc* rays, int64_t n, double t_min, double t_max,
+                 uint64_t seed, rt_hit_desc* out) {
+    if (!c || !s) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_batch: null argument");
+    if (n < 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_batch: negative count");
+    if (n == 0) return RT_OK;
+    if (!rays || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_batch: null buffer");
+    CU(cudaSetDevice(c->device));
+    std::vector<DevRayIn> h_in((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+        DevRayIn& r = h_in[k];
+        r.ox = (float)rays[k].origin[0]; r.oy = (float)rays[k].origin[1]; r.oz = (float)rays[k].origin[2];
+        r.dx = (float)rays[k].direction[0]; r.dy = (float)rays[k].direction[1]; r.dz = (float)rays[k].direction[2];
+        r.time = (float)rays[k].time; r.pad = 0.0f;
+    }
+    DevRayIn* d_in = nullptr;
+    DevHitOut* d_out = nullptr;
+    CU(cudaMalloc(&d_in, (size_t)n * sizeof(DevRayIn)));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n * sizeof(DevHitOut));
+    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc(hits)"); }
+    std::vector<DevHitOut> h_out((size_t)n);
+    e = cudaMemcpy(d_in, h_in.data(), (size_t)n * sizeof(DevRayIn), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        hit_kernel<<<(unsigned)((n + 127) / 128), 128>>>(s->dev, d_in, n, (float)t_min, (float)t_max, seed, d_out);
+        e = cudaMemcpy(h_out.data(), d_out, (size_t)n * sizeof(DevHitOut), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_hit_batch");
+    for (int64_t k = 0; k < n; ++k) {
+        const DevHitOut& h = h_out[k];
+        rt_hit_desc& o = out[k];
+        std::memset(&o, 0, sizeof(o));
+        o.hit = h.hit; o.front_face = h.front_face; o.prim_id = h.prim; o.mat_id = h.mat;
+        o.t = h.t; o.p[0] = h.px; o.p[1] = h.py; o.p[2] = h.pz;
+        o.normal[0] = h.nx; o.normal[1] = h.ny; o.normal[2] = h.nz;
+        o.u = h.u; o.v = h.v;
+    }
+    return RT_OK;
+}
+
+int rt_texture_batch(rt_context* c, const rt_scene* s, int tex, const double* uvp, int64_t n, double* rgb_out) {
+    if (!c || !s) return fail(RT_ERR_INVALID_ARGUMENT, "rt_texture_batch: null argument");
+    if (tex < 0 || (size_t)tex * 2 >= s->compiled.textures.size()) return fail(RT_ERR_OUT_OF_RANGE, "rt_texture_batch: unknown texture id");
+    if (n <= 0) return n == 0 ? RT_OK : fail(RT_ERR_INVALID_ARGUMENT, "rt_texture_batch: negative count");
+    if (!uvp || !rgb_out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_texture_batch: null buffer");
+    CU(cudaSetDevice(c->device));
+    std::vector<float> h_in((size_t)n * 5), h_out((size_t)n * 3);
+    for (int64_t k = 0; k < n * 5; ++k) h_in[k] = (float)uvp[k];
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, h_in.size() * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_out, h_out.size() * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
+    e = cudaMemcpy(d_in, h_in.data(), h_in.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cudaFuncSetAttribute(texture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes());
+        texture_kernel<<<(unsigned)((n + 127) / 128), 128, perlin_smem_bytes()>>>(s->dev, tex, d_in, n, d_out);
+        e = cudaMemcpy(h_out.data(), d_out, h_out.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_texture_batch");
+    for (int64_t k = 0; k < n * 3; ++k) rgb_out[k] = h_out[k];
+    return RT_OK;
+}
+
+int rt_get_ray_batch(rt_context* c, const rt_camera_desc* cam, const int64_t* pixel_index, const int64_t* sample_index,
+                     int64_t n, uint64_t seed, rt_ray_desc* out) {
+    if (!c || !cam) return fail(RT_ERR_INVALID_ARGUMENT, "rt_get_ray_batch: null argument");
+    if (n <= 0) return n == 0 ? RT_OK : fail(RT_ERR_INVALID_ARGUMENT, "rt_get_ray_batch: negative count");
+    if (!pixel_index || !sample_index || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_get_ray_batch: null buffer");
+    CU(cudaSetDevice(c->device));
+    int64_t *d_pix = nullptr, *d_smp = nullptr;
+    DevRayIn* d_out = nullptr;
+    CU(cudaMalloc(&d_pix, (size_t)n * 8));
+    cudaError_t e = cudaMalloc(&d_smp, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * sizeof(DevRayIn));
+    std::vector<DevRayIn> h((size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_pix, pixel_index, (size_t)n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_smp, sample_index, (size_t)n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        get_ray_kernel<<<(unsigned)((n + 127) / 128), 128>>>(make_dev_camera(*cam), d_pix, d_smp, n, seed, d_out);
+        e = cudaMemcpy(h.data(), d_out, (size_t)n * sizeof(DevRayIn), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_pix); cudaFree(d_smp); cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_get_ray_batch");
+    for (int64_t k = 0; k < n; ++k) {
+        out[k].origin[0] = h[k].ox; out[k].origin[1] = h[k].oy; out[k].origin[2] = h[k].oz;
+        out[k].direction[0] = h[k].dx; out[k].direction[1] = h[k].dy; out[k].direction[2] = h[k].dz;
+        out[k].time = h[k].time;
+    }
+    return RT_OK;
+}
+
+int rt_bvh_export(const rt_scene* s, int bvh_hittable, int32_t* object_of_node, int32_t capacity, int32_t* n_out) {
+    if (!s || !n_out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_bvh_export: null argument");
+    const CompiledScene& cs = s->compiled;
+    for (size_t k = 0; k < cs.bvh_hittable_ids.size(); ++k) {
+        if (cs.bvh_hittable_ids[k] != bvh_hittable) continue;
+        const auto& pre = cs.bvh_preorder_objects[k];
+        *n_out = (int32_t)pre.size();
+        if (object_of_node) {
+            if (capacity < (int32_t)pre.size()) return fail(RT_ERR_OUT_OF_RANGE, "rt_bvh_export: capacity too small");
+            std::memcpy(object_of_node, pre.data(), pre.size() * sizeof(int32_t));
+        }
+        return RT_OK;
+    }
+    return fail(RT_ERR_OUT_OF_RANGE, "rt_bvh_export: that hittable is not a BVH reachable from the world");
+}
+
+int rt_measure_fp32_peak(rt_context* c, double* tflops_out) {
+    if (!c || !tflops_out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_measure_fp32_peak: null argument");
+    CU(cudaSetDevice(c->device));
+    const int threads = 256, blocks = c->sm_count * 8, iters = 1 << 16;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)threads * blocks * sizeof(float)));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    fma_peak_kernel<<<blocks, threads>>>(d, 1024);   // warm-up
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(a);
+        fma_peak_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_measure_fp32_peak");
+    const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+    *tflops_out = flops / (best_ms * 1e-3) / 1e12;
+    return RT_OK;
+}
+
+}  // extern "C"

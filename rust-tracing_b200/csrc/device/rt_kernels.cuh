@@ -1,0 +1,524 @@
+// Device code of the ray_color hot path (renderer.rs:26-49,139-155 and everything it calls),
+// written for sm_100a. f32 arithmetic except where a primitive is flagged FLAG_PRECISE.
+//
+//   traverse<>()      world.hit(ray, ray_t): BVHNode / HittableList / Translate / RotateY /
+//                     Sphere / Quad / ConstantMedium (bvh.rs:90-113, hittable.rs:61-188,
+//                     sphere.rs:59-89, quad.rs:97-133, constant_medium.rs:34-70) as one stackless
+//                     loop over the threaded op stream (dev_scene.h)
+//   finalize_hit()    HitRecord::new + uv (hittable.rs:22-37, sphere.rs:48-52) for the winner only
+//   texture_value()   texture.rs:32-111 + perlin.rs:27-100 (tables in shared memory)
+//   shade()           Material::emitted / scatter (material.rs:26-138)
+//   camera_ray()      Camera::get_ray (camera.rs:112-137)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/rt_b200.h"
+#include "dev_scene.h"
+
+namespace rtdev {
+
+struct DevImage {
+    const float4* texels;  // pre-linearised (byte/255)^2.2 (color.rs:21-27), row 0 = top; one LDG.128 per lookup
+    int width, height;
+};
+
+struct DevScene {
+    const float4* ops;
+    int n_words;
+    const float4* mats;
+    const float4* texs;
+    const float4* perlin_vec;
+    const uint8_t* perlin_perm;
+    int n_perlin;
+    const double4* precise;
+    const DevImage* images;
+};
+
+struct DevCamera {
+    int width, height;
+    int max_depth;
+    float3 background;
+    float3 center;
+    float3 rel00;      // pixel00_loc - center (computed in f64 on the host: small, so f32 keeps sub-pixel accuracy)
+    float3 du, dv;
+    float3 disk_u, disk_v;
+    int defocus;
+};
+
+// ------------------------------------------------------------------ float3 helpers
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 f3(float4 v) { return make_float3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return a * s; }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float3 fma3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+__device__ __forceinline__ float3 normalize3(float3 a) { return a * rsqrtf(dot(a, a)); }
+__device__ __forceinline__ int fbits(float f) { return __float_as_int(f); }
+
+// ------------------------------------------------------------------ keyed RNG (shared spec with the oracle)
+// pcg4d (Jarzynski & Olano, JCGT 9(3) 2020). path key = pcg4d(pixel, sample, seed_lo, seed_hi);
+// draw(purpose) = pcg4d(key.x, key.y, key.z + segment, key.w + purpose); u01 = (x >> 8) * 2^-24.
+__device__ __forceinline__ uint4 pcg4d(uint4 v) {
+    v.x = v.x * 1664525u + 1013904223u; v.y = v.y * 1664525u + 1013904223u;
+    v.z = v.z * 1664525u + 1013904223u; v.w = v.w * 1664525u + 1013904223u;
+    v.x += v.y * v.w; v.y += v.z * v.x; v.z += v.x * v.y; v.w += v.y * v.z;
+    v.x ^= v.x >> 16; v.y ^= v.y >> 16; v.z ^= v.z >> 16; v.w ^= v.w >> 16;
+    v.x += v.y * v.w; v.y += v.z * v.x; v.z += v.x * v.y; v.w += v.y * v.z;
+    return v;
+}
+constexpr uint32_t P_CAMERA = 0, P_CAMERA_DISK = 1, P_SCATTER = 2, P_MEDIUM = 16;
+__device__ __forceinline__ uint4 path_key(uint64_t seed, uint32_t pixel, uint32_t sample) {
+    return pcg4d(make_uint4(pixel, sample, (uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ uint4 draw(uint4 key, uint32_t seg, uint32_t purpose) {
+    return pcg4d(make_uint4(key.x, key.y, key.z + seg, key.w + purpose));
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// loop-free samplers with the distributions of vec3.rs:54-65 (rejection loops in the reference)
+__device__ __forceinline__ float3 unit_vector(float u0, float u1) {
+    const float z = 1.0f - 2.0f * u0;
+    const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    sincospif(2.0f * u1, &s, &c);
+    return f3(r * c, r * s, z);
+}
+
+// ------------------------------------------------------------------ traversal
+struct Ray {
+    float3 o, d;
+    float time;
+};
+
+struct Best {
+    float t;
+    int op;   // word index of the winning primitive / medium op, -1 = none
+    int xf;   // word index of the enclosing OP_XFORM_ENTER, -1 = world space
+};
+
+__device__ __forceinline__ bool slab(float4 w0, float4 w1, float3 o, float3 inv, float tmin, float tmax) {
+    // AABB::hit (aabb.rs:64-84) as a tight slab test with the reciprocal hoisted per ray (permitted
+    // substitution, SURVEY.md §8(a)-Q: it only culls more, it never changes which hits exist).
+    const float tx0 = (w0.x - o.x) * inv.x, tx1 = (w1.x - o.x) * inv.x;
+    const float ty0 = (w0.y - o.y) * inv.y, ty1 = (w1.y - o.y) * inv.y;
+    const float tz0 = (w0.z - o.z) * inv.z, tz1 = (w1.z - o.z) * inv.z;
+    // fminf/fmaxf drop a NaN operand (0*inf when the origin lies on a slab of a parallel ray), like f64::min/max
+    const float t_enter = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+    const float t_exit = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
+    return t_enter <= t_exit * 1.0000012f + 1e-30f || t_enter <= t_exit;
+}
+
+__device__ __forceinline__ float3 safe_inv(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+
+// local = R(x - a) + b with R = rotate-y as in hittable.rs:164-168
+__device__ __forceinline__ float3 xform_point(float3 x, float4 w2, float4 w3) {
+    const float3 q = x - f3(w2);
+    const float s = w2.w, c = w3.w;
+    return f3(c * q.x - s * q.z + w3.x, q.y + w3.y, s * q.x + c * q.z + w3.z);
+}
+__device__ __forceinline__ float3 xform_dir(float3 v, float4 w2, float4 w3) {
+    const float s = w2.w, c = w3.w;
+    return f3(c * v.x - s * v.z, v.y, s * v.x + c * v.z);
+}
+// inverse rotation (hittable.rs:173-179)
+__device__ __forceinline__ float3 xform_dir_back(float3 v, float4 w2, float4 w3) {
+    const float s = w2.w, c = w3.w;
+    return f3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z);
+}
+
+// Sphere::hit roots (sphere.rs:59-83). Returns false on a miss; t receives the accepted root.
+// `self_origin`: the ray starts on this very sphere, so the root that is analytically 0 is dropped
+// (in f64 the reference rejects it through ray_t.min = 0.001; in f32 its rounding noise can exceed that).
+__device__ __forceinline__ bool sphere_roots_f32(float3 oc, float3 d, float r, bool self_origin, float* r1, float* r2) {
+    const float a = dot(d, d);
+    const float hb = dot(oc, d);
+    const float inv_a = 1.0f / a;
+    // discriminant/a = r^2 - |oc - (hb/a) d|^2 : no cancellation between hb^2 and a*c for distant origins
+    const float3 l = fma3(-hb * inv_a, d, oc);
+    const float disc = fmaf(r, r, -dot(l, l));
+    if (disc < 0.0f) return false;
+    const float sq = sqrtf(disc * a);
+    const float cc = fmaf(-r, r, dot(oc, oc));
+    float near_root, far_root;
+    if (hb > 0.0f) {            // both roots via q to avoid -hb + sq cancellation
+        const float q = -hb - sq;
+        near_root = q * inv_a;
+        far_root = self_origin ? __int_as_float(0x7fc00000) : cc / q;
+    } else {
+        const float q = -hb + sq;
+        far_root = q * inv_a;
+        near_root = self_origin ? __int_as_float(0x7fc00000) : cc / q;
+    }
+    *r1 = near_root;
+    *r2 = far_root;
+    return true;
+}
+__device__ __forceinline__ bool sphere_roots_f64(float3 o, float3 d, float time, const double4* pr, bool moving,
+                                                 bool self_origin, float* r1, float* r2) {
+    const double4 c = pr[0];
+    double cx = c.x, cy = c.y, cz = c.z;
+    if (moving) { const double4 v = pr[1]; cx += v.x * (double)time; cy += v.y * (double)time; cz += v.z * (double)time; }
+    const double ox = (double)o.x - cx, oy = (double)o.y - cy, oz = (double)o.z - cz;
+    const double dx = d.x, dy = d.y, dz = d.z;
+    const double a = dx * dx + dy * dy + dz * dz;
+    const double hb = ox * dx + oy * dy + oz * dz;
+    const double cc = ox * ox + oy * oy + oz * oz - c.w * c.w;
+    const double disc = hb * hb - a * cc;
+    if (disc < 0.0) return false;
+    const double sq = sqrt(disc);
+    double n = (-hb - sq) / a, f = (-hb + sq) / a;
+    if (self_origin) { if (hb > 0.0) f = __longlong_as_double(0x7ff8000000000000ll); else n = __longlong_as_double(0x7ff8000000000000ll); }
+    *r1 = (float)n;
+    *r2 = (float)f;
+    return true;
+}
+
+template <bool WORLD>
+__device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, const Ray& ray, float tmin, Best& best,
+                                         int origin_op, uint4 key, uint32_t seg);
+
+// Closest t of a medium's boundary program (t only; constant_medium.rs:35-39 needs nothing else).
+__device__ __noinline__ float boundary_closest_t(const DevScene& S, int begin, int end, const Ray& ray, float tmin, float tmax) {
+    Best b;
+    b.t = tmax; b.op = -1; b.xf = -1;
+    traverse<false>(S, begin, end, ray, tmin, b, -1, make_uint4(0, 0, 0, 0), 0u);
+    return b.op >= 0 ? b.t : __int_as_float(0x7fc00000);
+}
+
+template <bool WORLD>
+__device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, const Ray& ray, float tmin, Best& best,
+                                         int origin_op, uint4 key, uint32_t seg) {
+    float3 o = ray.o, d = ray.d;
+    float3 inv = safe_inv(d);
+    float3 so = o, sd = d;  // outer ray while inside an instance
+    int cur_xf = -1;
+    int i = begin;
+    const float4* __restrict__ ops = S.ops;
+    while (i < end) {
+        const float4 w0 = __ldg(ops + i);
+        const float4 w1 = __ldg(ops + i + 1);
+        const uint32_t hdr = (uint32_t)fbits(w0.w);
+        const uint32_t kind = hdr & 15u;
+        if (kind == OP_INNER) {
+            i = slab(w0, w1, o, inv, tmin, best.t) ? i + 2 : fbits(w1.w);
+        } else if (kind == OP_SPHERE) {
+            const uint32_t flags = (hdr >> 4) & 15u;
+            const bool moving = flags & FLAG_MOVING;
+            float r1, r2;
+            bool ok;
+            if (flags & FLAG_PRECISE) {
+                ok = sphere_roots_f64(o, d, ray.time, S.precise + 2 * fbits(w1.w), moving, i == origin_op, &r1, &r2);
+            } else {
+                float3 c = f3(w0);
+                if (moving) c = fma3(ray.time, f3(__ldg(ops + i + 2)), c);  // sphere.rs:53-55
+                ok = sphere_roots_f32(o - c, d, w1.x, i == origin_op, &r1, &r2);
+            }
+            if (ok) {
+                float root = r1;  // ray_t.surrounds: open interval (sphere.rs:78-83)
+                if (!(tmin < root && root < best.t)) root = r2;
+                if (tmin < root && root < best.t) { best.t = root; best.op = i; best.xf = cur_xf; }
+            }
+            i += moving ? 3 : 2;
+        } else if (kind == OP_QUAD) {
+            const float3 n = f3(w0);
+            const float denom = dot(n, d);
+            const float4 w3 = __ldg(ops + i + 3);
+            if (!(fabsf(denom) < 1e-8f) && i != origin_op) {       // quad.rs:110-112
+                const float t = (w3.x - dot(n, o)) / denom;
+                if (tmin <= t && t <= best.t) {                      // ray_t.contains: closed (quad.rs:115)
+                    const float4 w2 = __ldg(ops + i + 2);
+                    const float3 p = fma3(t, d, o);
+                    const float alpha = dot(f3(w1), p) + w1.w;
+                    const float beta = dot(f3(w2), p) + w2.w;
+                    if (!(alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f)) { best.t = t; best.op = i; best.xf = cur_xf; }
+                }
+            }
+            i += 4;
+        } else if (kind == OP_XFORM_ENTER) {
+            if (slab(w0, w1, o, inv, tmin, best.t)) {
+                const float4 w2 = __ldg(ops + i + 2), w3 = __ldg(ops + i + 3);
+                so = o; sd = d;
+                o = xform_point(o, w2, w3);     // hittable.rs:98,164-168
+                d = xform_dir(d, w2, w3);
+                inv = safe_inv(d);
+                cur_xf = i;
+                i += 4;
+            } else {
+                i = fbits(w1.w);
+            }
+        } else if (kind == OP_XFORM_EXIT) {
+            o = so; d = sd;
+            inv = safe_inv(d);
+            cur_xf = -1;
+            i += 2;
+        } else {  // OP_MEDIUM — constant_medium.rs:34-70
+            const int skip = fbits(w1.w);
+            if (WORLD && slab(w0, w1, o, inv, tmin, best.t)) {
+                const float4 w2 = __ldg(ops + i + 2);
+                const float4 w3 = __ldg(ops + i + 3);
+                float t1, t2;
+                bool ok;
+                if (fbits(w2.w) == MEDIUM_BOUNDARY_SPHERE) {
+                    const float4 w4 = __ldg(ops + i + 4);
+                    const uint32_t aux = (uint32_t)fbits(w4.w);
+                    const bool moving = (aux >> 24) & FLAG_MOVING;
+                    if ((aux >> 24) & FLAG_PRECISE) {
+                        ok = sphere_roots_f64(o, d, ray.time, S.precise + 2 * (aux & 0xffffffu), moving, false, &t1, &t2);
+                    } else {
+                        float3 c = f3(w3);
+                        if (moving) c = fma3(ray.time, f3(w4), c);
+                        ok = sphere_roots_f32(o - c, d, w3.w, false, &t1, &t2);
+                    }
+                    // hit1 over the universe takes the near root; hit2 needs a root > hit1.t + 0.0001
+                    ok = ok && (t2 > t1 + 0.0001f);
+                } else {
+                    Ray lr; lr.o = o; lr.d = d; lr.time = ray.time;
+                    const float inf = __int_as_float(0x7f800000);
+                    t1 = boundary_closest_t(S, fbits(w3.x), fbits(w3.y), lr, -inf, inf);
+                    ok = (t1 == t1);
+                    if (ok) { t2 = boundary_closest_t(S, fbits(w3.x), fbits(w3.y), lr, t1 + 0.0001f, inf); ok = (t2 == t2); }
+                }
+                if (ok) {
+                    t1 = fmaxf(t1, tmin);
+                    t2 = fminf(t2, best.t);
+                    if (t1 < t2) {
+                        t1 = fmaxf(t1, 0.0f);
+                        const float ray_length = sqrtf(dot(d, d));
+                        const float inside = (t2 - t1) * ray_length;
+                        const float u = u01(draw(key, seg, P_MEDIUM + (uint32_t)fbits(w2.z)).x);
+                        const float hit_distance = w2.x * logf(u);   // drawn only on this branch (constant_medium.rs:48)
+                        if (hit_distance <= inside) { best.t = t1 + hit_distance / ray_length; best.op = i; best.xf = cur_xf; }
+                    }
+                }
+            }
+            i = skip;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ hit record of the winner
+struct HitRec {
+    float3 p, normal;
+    float t, u, v;
+    int mat, prim;
+    bool front_face;
+    bool uv_lazy;       // sphere: u,v derived from `sn` only if a texture asks (sphere.rs:87 computes it always)
+    float3 sn;          // sphere outward normal in the sphere's own space
+};
+
+__device__ __forceinline__ void sphere_uv(float3 n, float* u, float* v) {   // sphere.rs:48-52
+    const float PI = 3.14159265358979323846f;
+    const float theta = acosf(-n.y);
+    const float phi = atan2f(-n.z, n.x) + PI;
+    *u = phi / (2.0f * PI);
+    *v = theta / PI;
+}
+
+__device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, const Best& best, HitRec& h) {
+    const float4* __restrict__ ops = S.ops;
+    float3 o = ray.o, d = ray.d;
+    float4 x2, x3;
+    if (best.xf >= 0) {
+        x2 = __ldg(ops + best.xf + 2); x3 = __ldg(ops + best.xf + 3);
+        o = xform_point(o, x2, x3);
+        d = xform_dir(d, x2, x3);
+    }
+    const float4 w0 = __ldg(ops + best.op), w1 = __ldg(ops + best.op + 1);
+    const uint32_t hdr = (uint32_t)fbits(w0.w);
+    const uint32_t kind = hdr & 15u;
+    const float t = best.t;
+    h.t = t;
+    h.uv_lazy = false;
+    h.u = 0.0f; h.v = 0.0f;
+    float3 outward;
+    if (kind == OP_SPHERE) {
+        const uint32_t flags = (hdr >> 4) & 15u;
+        const float3 pl = fma3(t, d, o);
+        if (flags & FLAG_PRECISE) {
+            const double4 c = S.precise[2 * fbits(w1.w)];
+            double cx = c.x, cy = c.y, cz = c.z;
+            if (flags & FLAG_MOVING) { const double4 cv = S.precise[2 * fbits(w1.w) + 1]; cx += cv.x * (double)ray.time; cy += cv.y * (double)ray.time; cz += cv.z * (double)ray.time; }
+            const double inv_r = 1.0 / c.w;
+            // hit point in f64 relative to the centre: keeps the normal of a huge sphere accurate
+            outward = f3((float)((((double)o.x - cx) + (double)t * (double)d.x) * inv_r),
+                         (float)((((double)o.y - cy) + (double)t * (double)d.y) * inv_r),
+                         (float)((((double)o.z - cz) + (double)t * (double)d.z) * inv_r));
+        } else {
+            float3 c = f3(w0);
+            if (flags & FLAG_MOVING) c = fma3(ray.time, f3(__ldg(ops + best.op + 2)), c);
+            outward = (pl - c) * (1.0f / w1.x);   // (p - center) / radius, reciprocal-multiply (vec3.rs:244-249)
+        }
+        h.mat = fbits(w1.y);
+        h.prim = fbits(w1.z);
+        h.uv_lazy = true;
+        h.sn = outward;
+    } else if (kind == OP_QUAD) {
+        const float4 w2 = __ldg(ops + best.op + 2), w3 = __ldg(ops + best.op + 3);
+        const float3 pl = fma3(t, d, o);
+        outward = f3(w0);
+        h.u = dot(f3(w1), pl) + w1.w;
+        h.v = dot(f3(w2), pl) + w2.w;
+        h.mat = fbits(w3.y);
+        h.prim = fbits(w3.z);
+    } else {  // OP_MEDIUM: HitRecord::new(r.at(t), phase, t, r, r.direction) (constant_medium.rs:52-58)
+        const float4 w2 = __ldg(ops + best.op + 2);
+        outward = d;
+        h.mat = fbits(w2.y);
+        h.prim = fbits(w2.z);
+    }
+    h.front_face = dot(d, outward) < 0.0f;                  // hittable.rs:23
+    float3 n = h.front_face ? outward : -outward;
+    if (best.xf >= 0) n = xform_dir_back(n, x2, x3);        // hittable.rs:176-179 (Translate leaves the normal alone)
+    h.normal = n;
+    h.p = fma3(t, ray.d, ray.o);                            // t is preserved by the instance transforms
+}
+
+// ------------------------------------------------------------------ textures
+struct PerlinShared {
+    const float4* vec;      // shared memory
+    const uint8_t* perm;    // shared memory
+};
+
+__device__ __forceinline__ float perlin_noise(const PerlinShared& P, int table, float3 p) {   // perlin.rs:27-50,81-100
+    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    const float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    const float uu = u * u * (3.0f - 2.0f * u);
+    const float vv = v * v * (3.0f - 2.0f * v);
+    const float ww = w * w * (3.0f - 2.0f * w);
+    const uint8_t* px = P.perm + table * 768;
+    const uint8_t* py = px + 256;
+    const uint8_t* pz = px + 512;
+    const float4* rv = P.vec + table * 256;
+    const int xi[2] = {px[i & 255], px[(i + 1) & 255]};
+    const int yi[2] = {py[j & 255], py[(j + 1) & 255]};
+    const int zi[2] = {pz[k & 255], pz[(k + 1) & 255]};
+    float acc = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float4 g = rv[xi[a] ^ yi[b] ^ zi[c]];
+                const float wa = a ? uu : 1.0f - uu, wb = b ? vv : 1.0f - vv, wc = c ? ww : 1.0f - ww;
+                acc += wa * wb * wc * (g.x * (u - (float)a) + g.y * (v - (float)b) + g.z * (w - (float)c));
+            }
+    return acc;
+}
+
+__device__ __forceinline__ float perlin_turbulence(const PerlinShared& P, int table, float3 p) {   // perlin.rs:52-64, depth 7
+    float acc = 0.0f, w = 1.0f;
+#pragma unroll 1
+    for (int o = 0; o < 7; ++o) {
+        acc = fmaf(w, perlin_noise(P, table, p), acc);
+        w *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(acc);
+}
+
+__device__ __forceinline__ float3 texture_value(const DevScene& S, const PerlinShared& P, int tex, HitRec& h) {
+    const float4* __restrict__ T = S.texs;
+    for (int guard = 0; guard < 16; ++guard) {
+        const float4 t0 = __ldg(T + 2 * tex);
+        const int kind = fbits(t0.x);
+        if (kind == RT_TEX_SOLID) {
+            return f3(__ldg(T + 2 * tex + 1));
+        } else if (kind == RT_TEX_CHECKER) {   // texture.rs:59-70
+            const int x = (int)floorf(t0.w * h.p.x), y = (int)floorf(t0.w * h.p.y), z = (int)floorf(t0.w * h.p.z);
+            tex = ((x + y + z) % 2 == 0) ? fbits(t0.y) : fbits(t0.z);
+        } else if (kind == RT_TEX_IMAGE) {     // texture.rs:82-93
+            if (h.uv_lazy) { sphere_uv(h.sn, &h.u, &h.v); h.uv_lazy = false; }
+            const DevImage im = S.images[fbits(t0.y)];
+            const float u = fminf(fmaxf(h.u, 0.0f), 1.0f);
+            const float v = 1.0f - fminf(fmaxf(h.v, 0.0f), 1.0f);
+            const uint32_t i = (uint32_t)(u * (float)(im.width - 1));
+            const uint32_t j = (uint32_t)(v * (float)(im.height - 1));
+            return f3(__ldg(im.texels + (size_t)j * im.width + i));
+        } else {                                // texture.rs:107-111
+            const float s = sinf(t0.w * h.p.z + 10.0f * perlin_turbulence(P, fbits(t0.y), h.p)) * 0.5f + 0.5f;
+            return f3(s, s, s);
+        }
+    }
+    return f3(0.0f, 0.0f, 0.0f);
+}
+
+// ------------------------------------------------------------------ materials
+__device__ __forceinline__ float3 reflect3(float3 v, float3 n) { return v - (2.0f * dot(v, n)) * n; }   // vec3.rs:91-93
+
+// Returns true if the path continues; updates ray and throughput, adds emission to L.
+__device__ __forceinline__ bool shade(const DevScene& S, const PerlinShared& P, Ray& ray, HitRec& h, uint4 key, uint32_t seg,
+                                      float3& L, float3& T) {
+    const float4 m0 = __ldg(S.mats + 2 * h.mat);
+    const int kind = fbits(m0.x);
+    if (kind == RT_MAT_DIFFUSE_LIGHT) {   // emitted (both faces) and no scatter: material.rs:114-122
+        L = L + T * texture_value(S, P, fbits(m0.y), h);
+        return false;
+    }
+    const uint4 r = draw(key, seg, P_SCATTER);
+    float3 dir, att;
+    if (kind == RT_MAT_LAMBERTIAN) {      // material.rs:27-41
+        dir = h.normal + unit_vector(u01(r.x), u01(r.y));
+        if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = h.normal;
+        att = texture_value(S, P, fbits(m0.y), h);
+    } else if (kind == RT_MAT_METAL) {    // material.rs:54-63
+        const float3 in_sphere = unit_vector(u01(r.x), u01(r.y)) * cbrtf(u01(r.z));
+        dir = reflect3(normalize3(ray.d), h.normal) + m0.z * in_sphere;
+        if (!(dot(dir, h.normal) > 0.0f)) return false;
+        att = f3(__ldg(S.mats + 2 * h.mat + 1));
+    } else if (kind == RT_MAT_DIELECTRIC) {   // material.rs:81-103
+        const float ratio = h.front_face ? 1.0f / m0.z : m0.z;
+        const float3 unit = normalize3(ray.d);
+        const float cos_theta = fminf(dot(-unit, h.normal), 1.0f);
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        float r0 = (1.0f - ratio) / (1.0f + ratio);
+        r0 = r0 * r0;
+        const float x = 1.0f - cos_theta;
+        const float refl = r0 + (1.0f - r0) * (x * x * x * x * x);           // material.rs:74-78
+        if (ratio * sin_theta > 1.0f || refl > u01(r.w)) {
+            dir = reflect3(unit, h.normal);
+        } else {                                                               // vec3.rs:96-101
+            const float3 perp = ratio * (unit + cos_theta * h.normal);
+            const float3 par = (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * h.normal;
+            dir = perp + par;
+        }
+        att = f3(1.0f, 1.0f, 1.0f);
+    } else {                               // isotropic: material.rs:132-138
+        dir = unit_vector(u01(r.x), u01(r.y));
+        att = texture_value(S, P, fbits(m0.y), h);
+    }
+    T = T * att;
+    ray.o = h.p;
+    ray.d = dir;
+    return true;
+}
+
+// ------------------------------------------------------------------ camera
+__device__ __forceinline__ Ray camera_ray(const DevCamera& C, int px, int py, uint4 key) {   // camera.rs:112-137
+    const uint4 r = draw(key, 0u, P_CAMERA);
+    const float sx = (float)px + (-0.5f + u01(r.x));
+    const float sy = (float)py + (-0.5f + u01(r.y));
+    float3 rel = fma3(sy, C.dv, fma3(sx, C.du, C.rel00));   // pixel_sample - center
+    Ray ray;
+    ray.o = C.center;
+    if (C.defocus) {
+        const uint4 e = draw(key, 0u, P_CAMERA_DISK);
+        const float rad = sqrtf(u01(e.x));
+        float s, c;
+        sincospif(2.0f * u01(e.y), &s, &c);
+        const float3 off = (rad * c) * C.disk_u + (rad * s) * C.disk_v;      // camera.rs:128-131
+        ray.o = C.center + off;
+        rel = rel - off;
+    }
+    ray.d = rel;
+    ray.time = u01(r.z);
+    return ray;
+}
+
+}  // namespace rtdev

@@ -1,0 +1,371 @@
+// rt_scene_desc (the reference's object graph, f64) -> threaded f32 op stream (dev_scene.h).
+// Host code, no CUDA. This is the "flatten" step the north star asks for: the BVH is built on
+// the host with the reference's split rule (scene_builder.cpp) and linearised here.
+#include "dev_scene.h"
+
+#include "../../../include/rt_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+
+namespace rtdev {
+namespace {
+
+struct Box {
+    double lo[3], hi[3];
+    bool valid = false;
+};
+
+Box box_union(const Box& a, const Box& b) {
+    if (!a.valid) return b;
+    if (!b.valid) return a;
+    Box r;
+    r.valid = true;
+    for (int c = 0; c < 3; ++c) {
+        r.lo[c] = std::fmin(a.lo[c], b.lo[c]);
+        r.hi[c] = std::fmax(a.hi[c], b.hi[c]);
+    }
+    return r;
+}
+
+float bits_to_float(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+float int_to_float_bits(int32_t i) { return bits_to_float((uint32_t)i); }
+
+// f64 -> f32 rounded outward with ~2 ulp of slack, so the f32 slab test stays conservative.
+float round_down(double v) {
+    float f = (float)v;
+    const float ninf = -std::numeric_limits<float>::infinity();
+    f = std::nextafterf(f, ninf);
+    return std::nextafterf(f, ninf);
+}
+float round_up(double v) {
+    float f = (float)v;
+    const float pinf = std::numeric_limits<float>::infinity();
+    f = std::nextafterf(f, pinf);
+    return std::nextafterf(f, pinf);
+}
+
+struct Compiler {
+    const rt_scene_desc* d;
+    CompiledScene* out;
+    std::string err;
+    int status = 0;
+    bool in_xform = false;
+    std::vector<Box> tight_hittable;  // memo, by hittable id
+    std::vector<Box> tight_node;      // memo, by bvh node index
+    std::vector<char> have_h, have_n;
+    double scale = 1.0;
+
+    bool fail(int code, const std::string& m) {
+        if (status == 0) { status = code; err = m; }
+        return false;
+    }
+
+    // Tight bounds of the geometry in the hittable's own (outer) space. The reference's list boxes
+    // always contain the origin (HittableList derives Default; hittable.rs:50-59) and its quad
+    // boxes are padded (aabb.rs:35-53); neither changes which hits exist, so the device uses the
+    // tight union (rounded outward) and culls more.
+    Box tight(int id) {
+        if (have_h[id]) return tight_hittable[id];
+        const rt_hittable_desc& h = d->hittables[id];
+        Box b;
+        switch (h.kind) {
+            case RT_HIT_SPHERE:
+            case RT_HIT_QUAD:
+                b.valid = true;
+                for (int c = 0; c < 3; ++c) { b.lo[c] = h.bbox[2 * c]; b.hi[c] = h.bbox[2 * c + 1]; }
+                break;
+            case RT_HIT_LIST:
+                for (int i = 0; i < h.count; ++i) b = box_union(b, tight(d->list_items[h.child + i]));
+                break;
+            case RT_HIT_TRANSLATE: {
+                const Box cb = tight(h.child);
+                b = cb;
+                if (cb.valid) for (int c = 0; c < 3; ++c) { b.lo[c] = cb.lo[c] + h.v0[c]; b.hi[c] = cb.hi[c] + h.v0[c]; }
+                break;
+            }
+            case RT_HIT_ROTATE_Y: {
+                const Box cb = tight(h.child);
+                if (cb.valid) {
+                    const double inf = std::numeric_limits<double>::infinity();
+                    b.valid = true;
+                    for (int c = 0; c < 3; ++c) { b.lo[c] = inf; b.hi[c] = -inf; }
+                    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 2; ++k) {
+                        const double x = i ? cb.hi[0] : cb.lo[0], y = j ? cb.hi[1] : cb.lo[1], z = k ? cb.hi[2] : cb.lo[2];
+                        const double p[3] = {h.s1 * x + h.s0 * z, y, -h.s0 * x + h.s1 * z};  // hittable.rs:137-138
+                        for (int c = 0; c < 3; ++c) { b.lo[c] = std::fmin(b.lo[c], p[c]); b.hi[c] = std::fmax(b.hi[c], p[c]); }
+                    }
+                }
+                break;
+            }
+            case RT_HIT_CONSTANT_MEDIUM:
+                b = tight(h.child);
+                break;
+            case RT_HIT_BVH:
+                b = tight_of_node(h.child);
+                break;
+        }
+        tight_hittable[id] = b;
+        have_h[id] = 1;
+        return b;
+    }
+    Box tight_of_node(int n) {
+        if (have_n[n]) return tight_node[n];
+        const rt_bvh_node_desc& node = d->bvh_nodes[n];
+        Box b = node.object >= 0 ? tight(node.object) : box_union(tight_of_node(node.left), tight_of_node(node.right));
+        tight_node[n] = b;
+        have_n[n] = 1;
+        return b;
+    }
+
+    int here() const { return (int)out->ops.size(); }
+    void push(float x, float y, float z, float w) { out->ops.push_back(F4{x, y, z, w}); }
+
+    // {lo.xyz, hdr} {hi.xyz, skip(patched later)}; returns index of word 1
+    int push_box_header(const Box& b, uint32_t hdr) {
+        if (b.valid) {
+            push(round_down(b.lo[0]), round_down(b.lo[1]), round_down(b.lo[2]), bits_to_float(hdr));
+            push(round_up(b.hi[0]), round_up(b.hi[1]), round_up(b.hi[2]), 0.0f);
+            for (int c = 0; c < 3; ++c)
+                if (std::isfinite(b.lo[c]) && std::isfinite(b.hi[c])) scale = std::fmax(scale, std::fmax(std::fabs(b.lo[c]), std::fabs(b.hi[c])));
+        } else {  // empty subtree: a box nothing can hit
+            const float inf = std::numeric_limits<float>::infinity();
+            push(inf, inf, inf, bits_to_float(hdr));
+            push(-inf, -inf, -inf, 0.0f);
+        }
+        return here() - 1;
+    }
+    void patch_skip(int word1) { out->ops[word1].w = int_to_float_bits(here()); }
+
+    int add_precise(const rt_hittable_desc& h) {
+        const int idx = (int)out->precise.size() / 2;
+        out->precise.push_back(D4{h.v0[0], h.v0[1], h.v0[2], h.s0});
+        out->precise.push_back(D4{h.v1[0], h.v1[1], h.v1[2], 0.0});
+        return idx;
+    }
+    static bool wants_precise(const rt_hittable_desc& h) { return std::fabs(h.s0) > 200.0; }
+
+    void emit_sphere(int id) {
+        const rt_hittable_desc& h = d->hittables[id];
+        uint32_t flags = 0;
+        if (h.flags & RT_FLAG_MOVING) flags |= FLAG_MOVING;
+        int pidx = 0;
+        if (wants_precise(h)) { flags |= FLAG_PRECISE; pidx = add_precise(h); }
+        push((float)h.v0[0], (float)h.v0[1], (float)h.v0[2], bits_to_float(make_hdr(OP_SPHERE, flags)));
+        push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), int_to_float_bits(pidx));
+        if (flags & FLAG_MOVING) push((float)h.v1[0], (float)h.v1[1], (float)h.v1[2], 0.0f);
+    }
+
+    void emit_quad(int id) {
+        const rt_hittable_desc& h = d->hittables[id];
+        const double* u = h.v1; const double* v = h.v2; const double* w = h.v3; const double* q = h.v0;
+        // alpha = w.(p x v) = p.(v x w);  beta = w.(u x p) = p.(w x u)   with p = hit - q
+        const double A[3] = {v[1] * w[2] - v[2] * w[1], v[2] * w[0] - v[0] * w[2], v[0] * w[1] - v[1] * w[0]};
+        const double B[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};
+        const double a0 = -(A[0] * q[0] + A[1] * q[1] + A[2] * q[2]);
+        const double b0 = -(B[0] * q[0] + B[1] * q[1] + B[2] * q[2]);
+        push((float)h.n[0], (float)h.n[1], (float)h.n[2], bits_to_float(make_hdr(OP_QUAD)));
+        push((float)A[0], (float)A[1], (float)A[2], (float)a0);
+        push((float)B[0], (float)B[1], (float)B[2], (float)b0);
+        push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), 0.0f);
+    }
+
+    void emit_node(int n, bool in_boundary) {
+        const rt_bvh_node_desc& node = d->bvh_nodes[n];
+        if (node.object >= 0) { emit(node.object, in_boundary); return; }
+        const int w1 = push_box_header(tight_of_node(n), make_hdr(OP_INNER));
+        emit_node(node.left, in_boundary);
+        emit_node(node.right, in_boundary);
+        patch_skip(w1);
+    }
+
+    void emit(int id, bool in_boundary) {
+        if (status) return;
+        if (id < 0 || id >= d->n_hittables) { fail(RT_ERR_OUT_OF_RANGE, "scene references an unknown hittable id"); return; }
+        const rt_hittable_desc& h = d->hittables[id];
+        switch (h.kind) {
+            case RT_HIT_SPHERE: emit_sphere(id); break;
+            case RT_HIT_QUAD: emit_quad(id); break;
+            case RT_HIT_LIST: {
+                if (h.count == 0) break;
+                const int w1 = push_box_header(tight(id), make_hdr(OP_INNER));
+                for (int i = 0; i < h.count; ++i) emit(d->list_items[h.child + i], in_boundary);
+                patch_skip(w1);
+                break;
+            }
+            case RT_HIT_TRANSLATE:
+            case RT_HIT_ROTATE_Y: {
+                if (in_xform) {
+                    fail(RT_ERR_UNSUPPORTED, "an instance (Translate/RotateY) nested inside another instance's subtree is not supported by the device layout");
+                    return;
+                }
+                // Fold the chain of directly nested Translate / RotateY wrappers (outermost first) into
+                // local = R(x - a) + b.
+                double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, s = 0.0, c = 1.0;
+                bool rotated = false;
+                int cur = id;
+                while (d->hittables[cur].kind == RT_HIT_TRANSLATE || d->hittables[cur].kind == RT_HIT_ROTATE_Y) {
+                    const rt_hittable_desc& x = d->hittables[cur];
+                    if (x.kind == RT_HIT_TRANSLATE) {
+                        if (!rotated && b[0] == 0 && b[1] == 0 && b[2] == 0) for (int k = 0; k < 3; ++k) a[k] += x.v0[k];
+                        else for (int k = 0; k < 3; ++k) b[k] -= x.v0[k];
+                    } else {
+                        const double s2 = x.s0, c2 = x.s1;
+                        const double bx = c2 * b[0] - s2 * b[2], bz = s2 * b[0] + c2 * b[2];
+                        b[0] = bx; b[2] = bz;
+                        if (!rotated) { s = s2; c = c2; }
+                        else { const double ns = s * c2 + c * s2, nc = c * c2 - s * s2; s = ns; c = nc; }
+                        rotated = true;
+                    }
+                    cur = x.child;
+                }
+                const int w1 = push_box_header(tight(id), make_hdr(OP_XFORM_ENTER));
+                push((float)a[0], (float)a[1], (float)a[2], (float)s);
+                push((float)b[0], (float)b[1], (float)b[2], (float)c);
+                in_xform = true;
+                emit(cur, in_boundary);
+                in_xform = false;
+                push(0.0f, 0.0f, 0.0f, bits_to_float(make_hdr(OP_XFORM_EXIT)));
+                push(0.0f, 0.0f, 0.0f, 0.0f);
+                patch_skip(w1);
+                break;
+            }
+            case RT_HIT_CONSTANT_MEDIUM: {
+                if (in_boundary) { fail(RT_ERR_UNSUPPORTED, "a ConstantMedium used as the boundary of another medium is not supported"); return; }
+                const rt_hittable_desc& bd = d->hittables[h.child];
+                const int w1 = push_box_header(tight(id), make_hdr(OP_MEDIUM));
+                if (bd.kind == RT_HIT_SPHERE) {
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), int_to_float_bits(MEDIUM_BOUNDARY_SPHERE));
+                    uint32_t pidx = 0;
+                    const bool precise = wants_precise(bd);
+                    if (precise) pidx = (uint32_t)add_precise(bd);
+                    push((float)bd.v0[0], (float)bd.v0[1], (float)bd.v0[2], (float)bd.s0);
+                    const uint32_t aux = ((bd.flags & RT_FLAG_MOVING) ? FLAG_MOVING : 0u) | (precise ? FLAG_PRECISE : 0u);
+                    push((float)bd.v1[0], (float)bd.v1[1], (float)bd.v1[2], int_to_float_bits((int32_t)(pidx | (aux << 24))));
+                } else {
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), int_to_float_bits(MEDIUM_BOUNDARY_PROGRAM));
+                    const int w3 = here();
+                    push(0.0f, 0.0f, 0.0f, 0.0f);
+                    const int bbegin = here();
+                    emit(h.child, true);
+                    out->ops[w3].x = int_to_float_bits(bbegin);
+                    out->ops[w3].y = int_to_float_bits(here());
+                }
+                patch_skip(w1);
+                break;
+            }
+            case RT_HIT_BVH: {
+                out->bvh_hittable_ids.push_back(id);
+                std::vector<int32_t> pre;
+                collect_preorder(h.child, &pre);
+                out->bvh_preorder_objects.push_back(pre);
+                emit_node(h.child, in_boundary);
+                break;
+            }
+            default:
+                fail(RT_ERR_INVALID_ARGUMENT, "unknown hittable kind");
+        }
+    }
+
+    void collect_preorder(int n, std::vector<int32_t>* o) {
+        const rt_bvh_node_desc& node = d->bvh_nodes[n];
+        o->push_back(node.object);
+        if (node.object < 0) { collect_preorder(node.left, o); collect_preorder(node.right, o); }
+    }
+};
+
+}  // namespace
+
+int compile_scene(const rt_scene_desc* desc, CompiledScene* out, const char** err) {
+    static thread_local std::string msg;
+    if (!desc || !out) { msg = "compile_scene: null argument"; if (err) *err = msg.c_str(); return RT_ERR_INVALID_ARGUMENT; }
+    if (desc->abi_version != RT_B200_ABI_VERSION) { msg = "rt_scene_desc.abi_version mismatch"; if (err) *err = msg.c_str(); return RT_ERR_INVALID_ARGUMENT; }
+    Compiler c;
+    c.d = desc;
+    c.out = out;
+    c.tight_hittable.resize(desc->n_hittables);
+    c.have_h.assign(desc->n_hittables, 0);
+    c.tight_node.resize(desc->n_bvh_nodes);
+    c.have_n.assign(desc->n_bvh_nodes, 0);
+
+    // validate references once so the emitters can index freely
+    for (int i = 0; i < desc->n_hittables && !c.status; ++i) {
+        const rt_hittable_desc& h = desc->hittables[i];
+        auto bad = [&](const char* m) { c.fail(RT_ERR_OUT_OF_RANGE, m); };
+        switch (h.kind) {
+            case RT_HIT_SPHERE: case RT_HIT_QUAD:
+                if (h.mat < 0 || h.mat >= desc->n_materials) bad("primitive references an unknown material");
+                break;
+            case RT_HIT_LIST:
+                if (h.count < 0 || h.child < 0 || h.child + h.count > desc->n_list_items) bad("list range out of bounds");
+                else for (int k = 0; k < h.count; ++k) { const int it = desc->list_items[h.child + k]; if (it < 0 || it >= i) { bad("list item must be an earlier hittable"); break; } }
+                break;
+            case RT_HIT_TRANSLATE: case RT_HIT_ROTATE_Y:
+                if (h.child < 0 || h.child >= i) bad("instance child must be an earlier hittable");
+                break;
+            case RT_HIT_CONSTANT_MEDIUM:
+                if (h.child < 0 || h.child >= i) bad("medium boundary must be an earlier hittable");
+                else if (h.mat < 0 || h.mat >= desc->n_materials) bad("medium references an unknown material");
+                break;
+            case RT_HIT_BVH:
+                if (h.child < 0 || h.child >= desc->n_bvh_nodes) bad("bvh root out of bounds");
+                break;
+            default: c.fail(RT_ERR_INVALID_ARGUMENT, "unknown hittable kind");
+        }
+    }
+    for (int i = 0; i < desc->n_bvh_nodes && !c.status; ++i) {
+        const rt_bvh_node_desc& n = desc->bvh_nodes[i];
+        if (n.object >= 0) { if (n.object >= desc->n_hittables) c.fail(RT_ERR_OUT_OF_RANGE, "bvh leaf references an unknown hittable"); }
+        else if (n.left <= i || n.right <= i || n.left >= desc->n_bvh_nodes || n.right >= desc->n_bvh_nodes)
+            c.fail(RT_ERR_OUT_OF_RANGE, "bvh children must follow their parent (pre-order)");
+    }
+    for (int i = 0; i < desc->n_materials && !c.status; ++i) {
+        const rt_material_desc& m = desc->materials[i];
+        const bool needs_tex = m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT || m.kind == RT_MAT_ISOTROPIC;
+        if (needs_tex && (m.tex < 0 || m.tex >= desc->n_textures)) c.fail(RT_ERR_OUT_OF_RANGE, "material references an unknown texture");
+    }
+    for (int i = 0; i < desc->n_textures && !c.status; ++i) {
+        const rt_texture_desc& t = desc->textures[i];
+        if (t.kind == RT_TEX_CHECKER && (t.a < 0 || t.a >= i || t.b < 0 || t.b >= i)) c.fail(RT_ERR_OUT_OF_RANGE, "checker children must be earlier textures");
+        if (t.kind == RT_TEX_IMAGE && (t.a < 0 || t.a >= desc->n_images)) c.fail(RT_ERR_OUT_OF_RANGE, "texture references an unknown image");
+        if (t.kind == RT_TEX_NOISE && (t.a < 0 || t.a >= desc->n_perlins)) c.fail(RT_ERR_OUT_OF_RANGE, "texture references an unknown perlin table");
+    }
+    if (!c.status && (desc->world < 0 || desc->world >= desc->n_hittables)) c.fail(RT_ERR_OUT_OF_RANGE, "world id out of range");
+
+    if (!c.status) c.emit(desc->world, false);
+    if (!c.status && out->ops.empty()) {  // empty world: one unhittable node keeps the kernels branch-free
+        const float inf = std::numeric_limits<float>::infinity();
+        out->ops.push_back(F4{inf, inf, inf, bits_to_float(make_hdr(OP_INNER))});
+        out->ops.push_back(F4{-inf, -inf, -inf, int_to_float_bits(2)});
+    }
+    if (c.status) { msg = c.err; if (err) *err = msg.c_str(); return c.status; }
+
+    for (int i = 0; i < desc->n_materials; ++i) {
+        const rt_material_desc& m = desc->materials[i];
+        out->materials.push_back(F4{int_to_float_bits(m.kind), int_to_float_bits(m.tex), (float)m.param, 0.0f});
+        out->materials.push_back(F4{(float)m.albedo[0], (float)m.albedo[1], (float)m.albedo[2], 0.0f});
+    }
+    for (int i = 0; i < desc->n_textures; ++i) {
+        const rt_texture_desc& t = desc->textures[i];
+        out->textures.push_back(F4{int_to_float_bits(t.kind), int_to_float_bits(t.a), int_to_float_bits(t.b), (float)t.scale});
+        out->textures.push_back(F4{(float)t.color[0], (float)t.color[1], (float)t.color[2], 0.0f});
+    }
+    out->n_perlin = desc->n_perlins;
+    for (int i = 0; i < desc->n_perlins; ++i) {
+        const rt_perlin_desc& p = desc->perlins[i];
+        for (int k = 0; k < 256; ++k) out->perlin_vec.push_back(F4{(float)p.ranvec[k][0], (float)p.ranvec[k][1], (float)p.ranvec[k][2], 0.0f});
+        for (int k = 0; k < 256; ++k) out->perlin_perm.push_back((uint8_t)p.perm_x[k]);
+        for (int k = 0; k < 256; ++k) out->perlin_perm.push_back((uint8_t)p.perm_y[k]);
+        for (int k = 0; k < 256; ++k) out->perlin_perm.push_back((uint8_t)p.perm_z[k]);
+    }
+    out->scene_scale = (float)c.scale;
+    return 0;
+}
+
+}  // namespace rtdev
