@@ -1,0 +1,223 @@
+"""GPU parity, part 2: the render loop (renderer.rs:26-49,139-155), textures, camera and post-process."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import small_scene
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LUM = np.array([0.2126, 0.7152, 0.0722])
+
+
+def agreement(dev, ref, spp, tol=1e-3):
+    rel = np.abs(dev[..., :3] - ref) / (np.abs(ref) + tol * spp)
+    return float((rel.max(axis=2) < tol).mean())
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_low_spp_pathwise_agreement(rt, ob, ctx, earth, idx):
+    """With the shared keyed RNG the f32 device and the f64 oracle trace the same paths up to rounding:
+    at 4 spp at least 98.5% of the pixels agree to 1e-3 relative (the rest are branch flips at grazing hits),
+    and the image means agree to 0.5%."""
+    s, cam = small_scene(rt, idx, earth)
+    ds = ctx.upload(s)
+    spp = 4
+    ref, _ = ob.render(s.desc, cam, 0, spp, seed=0, mode=0)
+    dev = ctx.render(ds, cam, 0, spp, seed=0)
+    assert np.all(dev[..., 3] == spp)
+    assert np.isfinite(dev).all() and dev.min() >= 0.0
+    assert agreement(dev, ref, spp) >= 0.985
+    assert dev[..., :3].mean() == pytest.approx(ref.mean(), rel=5e-3)
+    ds.close()
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_render_against_golden_fixture(rt, ctx, idx):
+    name = rt.SCENE_NAMES[idx]
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    s, cs = rt.builtin_scene(name, image_width=int(g["width"]), earth=rt.synthetic_earth(256, 128, seed=11))
+    cam = rt.Camera(cs)
+    ds = ctx.upload(s)
+    dev = ctx.render(ds, cam, 0, 4, seed=0)
+    assert agreement(dev, g["image_sum_4spp"], 4) >= 0.98
+    assert dev[..., :3].mean() == pytest.approx(g["image_sum_4spp"].mean(), rel=1e-2)
+    ds.close()
+
+
+@pytest.mark.parametrize("idx", [0, 3, 6, 7, 8])
+def test_converged_image_statistics(rt, ob, ctx, earth, idx):
+    """Independent seeds: oracle at N_ref spp vs device at N_gpu spp. Per-pixel luminance RMSE must stay within
+    1.5 x the Monte-Carlo standard error predicted from the oracle's own per-pixel sample variance, and the
+    mean luminance within 1% (SURVEY.md §8(d) image-parity protocol)."""
+    s, cam = small_scene(rt, idx, earth, width=96)
+    ds = ctx.upload(s)
+    n_ref, n_gpu = 64, 1024
+    ref, _, sq = ob.render(s.desc, cam, 0, n_ref, seed=11, mode=0, want_sumsq=True)
+    dev = ctx.render(ds, cam, 0, n_gpu, seed=12)
+    l_ref = (ref * LUM).sum(axis=2) / n_ref
+    l_dev = (dev[..., :3] * LUM).sum(axis=2) / n_gpu
+    var = (sq / n_ref - l_ref ** 2).clip(min=0) * n_ref / (n_ref - 1)
+    bound = 1.5 * np.sqrt(var.mean() * (1.0 / n_ref + 1.0 / n_gpu))
+    rmse = np.sqrt(((l_ref - l_dev) ** 2).mean())
+    assert rmse <= bound, (rmse, bound)
+    assert l_dev.mean() == pytest.approx(l_ref.mean(), rel=0.01 + 3 * np.sqrt(var.mean() / n_ref / l_ref.size) / l_ref.mean())
+    ds.close()
+
+
+def test_sample_range_semantics(rt, ob, ctx):
+    """rt_render(begin, count): disjoint ranges add up (live passes, resume, multi-GPU sharding), and a range
+    that does not start at 0 traces the same paths as the oracle's same range."""
+    s, cam = small_scene(rt, 6, width=64)
+    ds = ctx.upload(s)
+    full = ctx.render(ds, cam, 0, 12, seed=3)
+    a = ctx.render(ds, cam, 0, 5, seed=3)
+    b = ctx.render(ds, cam, 5, 7, seed=3)
+    assert np.allclose(a + b, full, rtol=2e-6, atol=1e-6)        # f32 atomics in a different order
+    ref, _ = ob.render(s.desc, cam, 5, 7, seed=3, mode=0)
+    assert agreement(b, ref, 7) >= 0.985
+    again = ctx.render(ds, cam, 0, 12, seed=3)
+    assert np.allclose(again, full, rtol=2e-6, atol=1e-6)
+    other = ctx.render(ds, cam, 0, 12, seed=4)
+    assert not np.allclose(other, full, rtol=1e-3)
+    ds.close()
+
+
+@pytest.mark.parametrize("w,aspect", [(1, 1.0), (13, 13 / 7), (8, 2.0), (33, 1.0), (5, 0.1)])
+def test_ragged_image_sizes(rt, ob, ctx, w, aspect):
+    """Sizes that are not a multiple of the 8x4 warp tile, down to a single pixel."""
+    s = rt.Scene()
+    m = s.Lambertian(s.CheckerTexture(0.5, (0.2, 0.3, 0.1), (0.9, 0.9, 0.9)))
+    l = rt.HittableList()
+    l.add(s.Sphere((0, -100.5, -1), 100.0, m))
+    l.add(s.Sphere((0, 0, -1), 0.5, s.Metal((0.8, 0.6, 0.2), 0.3)))
+    s.finish(s.BVHNode(l))
+    cam = rt.Camera(rt.CameraSettings(image_width=w, aspect_ratio=aspect, samples_per_pixel=6, max_depth=10,
+                                      background=(0.7, 0.8, 1.0)))
+    ds = ctx.upload(s)
+    dev = ctx.render(ds, cam, 0, 6, seed=1)
+    ref, _ = ob.render(s.desc, cam, 0, 6, seed=1, mode=0)
+    assert dev.shape[:2] == ref.shape[:2] == cam.shape
+    assert np.all(dev[..., 3] == 6)
+    assert np.allclose(dev[..., :3], ref, rtol=2e-2, atol=2e-2) or agreement(dev, ref, 6) >= 0.9
+    ds.close()
+
+
+def test_depth_exhaustion_and_lights_on_device(rt, ctx):
+    s = rt.Scene()
+    s.finish(s.Sphere((0, 0, 0), 5.0, s.Lambertian(s.SolidColor(1, 1, 1))))
+    cam = rt.Camera(rt.CameraSettings(image_width=16, aspect_ratio=1.0, samples_per_pixel=4, max_depth=5,
+                                      background=(0.7, 0.8, 1.0)))
+    ds = ctx.upload(s)
+    img = ctx.render(ds, cam, 0, 4)
+    assert img[..., :3].max() == 0.0 and np.all(img[..., 3] == 4)      # renderer.rs:140-142
+    st = ctx.stats()
+    assert st["paths"] == 16 * 16 * 4 and st["segments"] == 5 * st["paths"]
+    ds.close()
+    s2 = rt.Scene()
+    s2.finish(s2.Quad((-50, -50, -5), (100, 0, 0), (0, 100, 0), s2.DiffuseLight(s2.SolidColor(4, 3, 2))))
+    ds2 = ctx.upload(s2)
+    for z in (0.0, -10.0):    # both faces emit (material.rs:119-121)
+        cam2 = rt.Camera(rt.CameraSettings(image_width=8, aspect_ratio=1.0, samples_per_pixel=3, max_depth=5,
+                                           look_from=(0, 0, z), look_at=(0, 0, -5)))
+        img2 = ctx.render(ds2, cam2, 0, 3)
+        assert np.array_equal(img2[..., :3], np.broadcast_to(np.float32([12, 9, 6]), img2[..., :3].shape))
+    ds2.close()
+
+
+def test_textures_against_golden(rt, ctx):
+    g = np.load(os.path.join(GOLD, "textures.npz"))
+    earth = rt.synthetic_earth(256, 128, seed=11)
+    s = rt.Scene()
+    t_chk = s.CheckerTexture(0.32, (0.2, 0.3, 0.1), (0.9, 0.9, 0.9))
+    t_img = s.ImageTexture(earth)
+    t_noise = s.NoiseTexture(4.0, perlin_seed=3)
+    s.finish(s.Sphere((0, 0, 0), 1.0, s.Lambertian(t_noise)))
+    ds = ctx.upload(s)
+    uvp = g["uvp"]
+    chk = ctx.texture_batch(ds, t_chk, uvp)
+    # cell index floor(p/0.32): f32 can only disagree within a few ulp of a cell boundary
+    cell = uvp[:, 2:] / 0.32
+    safe = (np.abs(cell - np.round(cell)) > 1e-4).all(axis=1)
+    assert np.allclose(chk[safe], g["checker"][safe], atol=1e-7) and safe.mean() > 0.99
+    img = ctx.texture_batch(ds, t_img, uvp)
+    exact = np.isclose(img, g["image"], rtol=2e-6, atol=1e-7).all(axis=1)
+    assert exact.mean() >= 0.995                     # nearest-texel index flips only at texel edges
+    assert exact[:8].all()                           # corners, clamping (texture.rs:84-89)
+    noise = ctx.texture_batch(ds, t_noise, uvp)
+    assert np.abs(noise - g["noise"]).max() <= 2e-3 and np.abs(noise - g["noise"]).mean() <= 1e-4
+    ds.close()
+
+
+@pytest.mark.parametrize("name", ["random_balls", "final_scene"])
+def test_camera_rays_against_golden(rt, ctx, name):
+    g = np.load(os.path.join(GOLD, f"camera_{name}.npz"))
+    _, cs = rt.builtin_scene(name, image_width=int(g["width"]), earth=rt.synthetic_earth(256, 128, seed=11))
+    cam = rt.Camera(cs)
+    rays = ctx.get_ray_batch(cam, g["pixel"], g["sample"], seed=0)
+    assert np.array_equal(rays["time"], g["rays"]["time"])                       # 24-bit uniforms are exact in both
+    scale = np.abs(g["rays"]["origin"]).max()
+    assert np.abs(rays["origin"] - g["rays"]["origin"]).max() <= 4 * 2.0 ** -23 * scale
+    dscale = np.linalg.norm(g["rays"]["direction"], axis=1, keepdims=True)
+    assert (np.abs(rays["direction"] - g["rays"]["direction"]) / dscale).max() <= 8 * 2.0 ** -23
+
+
+def test_finalize_rgb8(rt, ob, ctx):
+    """color_to_rgb(sum/spp) on the device vs the oracle (color.rs:12-19): identical bytes except where
+    x^(1/2.2)*256 lands within f32 rounding of an integer."""
+    import torch
+    rng = np.random.default_rng(2)
+    n, spp = 50_000, 10.0
+    sums = rng.random((n, 4)).astype(np.float32) * 14.0
+    sums[:5, :3] = [[0, 0, 0], [10, 10, 10], [5, 2, 40], [np.nan, -1, 1e9], [2, 2, 2]]
+    t = torch.from_numpy(sums).cuda()
+    dev = ctx.finalize_rgb8(t.data_ptr(), n, spp)
+    ref = ob.finalize_rgb8(sums[:, :3].astype(np.float64), spp)
+    assert (dev == ref).mean() >= 0.999
+    assert np.abs(dev.astype(int) - ref.astype(int)).max() <= 1
+    assert tuple(dev[0]) == (0, 0, 0) and tuple(dev[1]) == (255, 255, 255) and tuple(dev[3]) == (0, 0, 255)
+    assert tuple(dev[4]) == tuple(ref[4]) == (123, 123, 123)
+
+
+FULL = {"cfg1_random_balls": (0, 400, 50), "cfg2a_checker": (1, 800, 0), "cfg2b_earth": (2, 800, 0),
+        "cfg2c_perlin": (3, 800, 0), "cfg3_cornell_box": (6, 600, 50), "cfg4_cornell_smoke": (7, 600, 0),
+        "cfg5_final_scene": (8, 800, 0)}
+
+
+@pytest.mark.parametrize("cfg", list(FULL))
+def test_full_size_properties(rt, ctx, earth, cfg):
+    """BASELINE.json's full image sizes (reduced spp): size-independent properties of the SUM framebuffer —
+    every pixel received exactly spp samples, sums are finite and non-negative, disjoint sample ranges add up,
+    the same seed reproduces the image, and the path count is W*H*spp."""
+    idx, width, depth = FULL[cfg]
+    s, cs = rt.builtin_scene(idx, image_width=width, max_depth=depth, earth=earth)
+    cam = rt.Camera(cs)
+    ds = ctx.upload(s)
+    spp = 8
+    full = ctx.render(ds, cam, 0, spp, seed=5)
+    st = ctx.stats()
+    h, w = cam.shape
+    assert st["paths"] == h * w * spp and st["segments"] >= st["paths"]
+    assert np.all(full[..., 3] == spp) and np.isfinite(full).all() and full.min() >= 0
+    a = ctx.render(ds, cam, 0, 3, seed=5)
+    b = ctx.render(ds, cam, 3, 5, seed=5)
+    assert np.allclose(a + b, full, rtol=3e-6, atol=1e-6)
+    assert np.allclose(ctx.render(ds, cam, 0, spp, seed=5), full, rtol=3e-6, atol=1e-6)
+    ds.close()
+
+
+def test_multi_gpu_sharding_on_one_gpu(rt, ctx):
+    """The 8-rank sample split rendered rank after rank on one GPU and summed equals the single-rank image."""
+    from rust_tracing_b200.distributed import shard_samples
+    s, cam = small_scene(rt, 7, width=80)
+    ds = ctx.upload(s)
+    spp = 37
+    full = ctx.render(ds, cam, 0, spp, seed=9)
+    acc = np.zeros_like(full)
+    for r in range(8):
+        b, c = shard_samples(spp, r, 8)
+        if c:
+            acc += ctx.render(ds, cam, b, c, seed=9)
+    assert np.allclose(acc, full, rtol=3e-6, atol=1e-6)
+    ds.close()
