@@ -299,6 +299,12 @@ typedef struct rt_render_stats {
 } rt_render_stats;
 int rt_render_get_stats(rt_context* ctx, rt_render_stats* out);
 
+/* Instrumented run of the same kernel: counts the ops the device traversal executes (box tests, sphere tests,
+ * quad tests, shades by material, ...) over the given sample range. counters[] receives the counts (returns how
+ * many), *names_csv their comma-separated names. Used to state the device's own algorithmic flops per path. */
+int rt_render_count_ops(rt_context* ctx, const rt_scene* scene, const rt_camera_desc* cam, int64_t sample_begin,
+                        int64_t sample_count, uint64_t seed, uint64_t* counters, int capacity, const char** names_csv);
+
 /* Parity entry points (host in, host out, synchronous). */
 int rt_hit_batch(rt_context* ctx, const rt_scene* scene, const rt_ray_desc* rays, int64_t n,
                  double t_min, double t_max, uint64_t seed, rt_hit_desc* out);

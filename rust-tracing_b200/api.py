@@ -321,6 +321,14 @@ class Context:
         return {"paths": st.paths, "segments": st.segments, "kernel_launches": st.kernel_launches,
                 "last_kernel_ms": st.last_kernel_ms}
 
+    def count_ops(self, dscene, cam, sample_begin=0, sample_count=1, seed=0):
+        """Op counts of the instrumented kernel over a sample range (dict name -> count)."""
+        buf = np.zeros(64, dtype=np.uint64)
+        names = C.c_char_p()
+        n = A.check(self._lib.rt_render_count_ops(self._h, dscene._h, C.byref(cam), sample_begin, sample_count, seed,
+                                                  buf.ctypes.data, len(buf), C.byref(names)))
+        return dict(zip(names.value.decode().split(","), (int(x) for x in buf[:n])))
+
     def hit_batch(self, dscene, rays, t_min=0.001, t_max=float("inf"), seed=7):
         rays = np.ascontiguousarray(rays, dtype=A.ray_dtype())
         out = np.zeros(len(rays), dtype=A.hit_dtype())

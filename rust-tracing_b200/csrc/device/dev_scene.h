@@ -27,10 +27,13 @@ enum OpKind : uint32_t {
     OP_XFORM_ENTER = 3,  // w0 = {lo.xyz, hdr}  w1 = {hi.xyz, skip} w2 = {a.xyz, sin} w3 = {b.xyz, cos}       size 4
                          //   local = R(x - a) + b, R = rotate-y (hittable.rs:164-168); skip = word after the matching exit
     OP_XFORM_EXIT = 4,   // w0 = {0,0,0, hdr}   w1 = {0,0,0,0}                           size 2
-    OP_MEDIUM = 5,       // w0 = {lo.xyz, hdr}  w1 = {hi.xyz, skip} w2 = {neg_inv_density, mat, prim_id, bkind}
-                         // w3 = {bbegin, bend, 0, 0} (bkind 1: word range of the boundary program, which follows inline)
-                         //   bkind 0: boundary is a sphere: w3 = {c.xyz, r}, w4 = {center_vec.xyz, precise_idx}  (size 5)
-    OP_BOX = 6,          // cube list as one slab primitive: w0 = {min.xyz, hdr} w1 = {max.xyz, mat} w2 = {first_quad_prim_id,0,0,0}  size 3
+    OP_MEDIUM = 5,       // body of a ConstantMedium; always preceded by an OP_INNER holding its box (skip = past the medium)
+                         // w0 = {neg_inv_density, mat, prim_id, hdr(flags = boundary kind)}
+                         //   boundary sphere : w1 = {c.xyz, r}  w2 = {center_vec.xyz, precise_idx | aux<<24}             size 3
+                         //   boundary program: w1 = {bbegin, bend, 0, 0} w2 = {0}; the program follows inline, next = bend size 3
+                         //   boundary xbox   : w1 = {a.xyz, sin} w2 = {b.xyz, cos} w3 = {min.xyz, 0} w4 = {max.xyz, 0}   size 5
+    OP_BOX = 6,          // a Quad::cube list as ONE slab primitive: w0 = {min.xyz, hdr} w1 = {max.xyz, mat} w2 = {first_quad_prim_id, 0, 0, 0}  size 3
+                         //   faces in quad.rs:45-93 order: 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y ; prim_id = first + face
 };
 
 constexpr uint32_t FLAG_MOVING = 1u;   // sphere has center_vec
@@ -38,15 +41,27 @@ constexpr uint32_t FLAG_PRECISE = 2u;  // sphere test runs in f64 (huge radius; 
 
 constexpr int MEDIUM_BOUNDARY_SPHERE = 0;
 constexpr int MEDIUM_BOUNDARY_PROGRAM = 1;
+constexpr int MEDIUM_BOUNDARY_XBOX = 2;
+constexpr int kMaxHoistedMedia = 8;   // [Translate/RotateY chain of] a cube: entry/exit from one slab test in the cube's frame
 
-inline uint32_t make_hdr(uint32_t kind, uint32_t flags = 0, uint32_t aux = 0) { return kind | (flags << 4) | (aux << 8); }
+// header bits: [0,4) kind, [4,8) flags, [8,11) class of the op reached by falling through, [11,14) class of the op
+// reached through the skip link (equal to the fall-through class for ops without one). Knowing the next op's class
+// before its words arrive lets the render kernel vote on what to run next without waiting for the load.
+inline uint32_t make_hdr(uint32_t kind, uint32_t flags = 0) { return kind | (flags << 4); }
+
+enum OpClass : uint32_t { CLS_SLAB = 0, CLS_SPHERE = 1, CLS_QUAD = 2, CLS_MEDIUM = 3, CLS_SHADE = 4, CLS_IDLE = 5 };
+inline uint32_t class_of_kind(uint32_t kind) {
+    return kind == OP_SPHERE ? CLS_SPHERE : kind == OP_QUAD ? CLS_QUAD : kind == OP_MEDIUM ? CLS_MEDIUM : CLS_SLAB;
+}
 
 struct F4 { float x, y, z, w; };
 struct D4 { double x, y, z, w; };
 
 // Output of compile_scene (host memory), uploaded verbatim.
 struct CompiledScene {
-    std::vector<F4> ops;         // the op stream; world program = [0, ops.size())
+    std::vector<F4> ops;         // the op stream: world program = [0, n_world_words), then the hoisted media bodies
+    int n_world_words = 0;
+    std::vector<int32_t> hoisted_media;   // word indices (>= n_world_words) of OP_MEDIUM bodies evaluated at segment start
     std::vector<F4> materials;   // 2 words each: {kind, tex, param, 0} {albedo.xyz, 0}
     std::vector<F4> textures;    // 2 words each: {kind, a, b, scale} {color.xyz, 0}
     std::vector<F4> perlin_vec;  // 256 per table: {ranvec.xyz, 0}
@@ -57,9 +72,15 @@ struct CompiledScene {
     std::vector<int32_t> bvh_hittable_ids;
     std::vector<std::vector<int32_t>> bvh_preorder_objects;
     float scene_scale = 1.0f;    // largest |coordinate| of finite geometry (parity tolerances)
+    uint32_t first_class = CLS_SHADE;   // class of op 0
+};
+
+struct CompileOptions {
+    bool box_primitives = true;   // false: emit cube lists as 6 quads (the reference's own structure), for A/B parity runs
+    bool hoist_media = true;      // false: media stay in the op stream at their BVH position
 };
 
 // Returns 0 or a negative rt_status; message in *err.
-int compile_scene(const rt_scene_desc* desc, CompiledScene* out, const char** err);
+int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, CompiledScene* out, const char** err);
 
 }  // namespace rtdev

@@ -12,8 +12,10 @@
 
 #include "../host/host_common.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,8 +40,20 @@ struct RenderParams {
     int n_chunks;
     float4* sum;          // W*H float4
     unsigned int* work_counter;
-    unsigned long long* stats;   // [0] paths, [1] segments
+    unsigned long long* stats;   // [0] paths, [1] segments, [2..] op counters (counting build only)
+    int first_class;             // OpClass of op 0
+    int shade_min;               // the shade class may win the vote once this many lanes wait for it
+    int slab_fast;               // v3: lanes in the slab class that skip the full vote
+    int slab_reps, sphere_reps;  // v3: consecutive ops a class may run per vote
 };
+
+// op counters of the instrumented kernel (rt_render_count_ops): what the device traversal actually executes
+enum Counter { K_PATHS = 0, K_SEGMENTS, K_SLAB, K_BOX, K_BOX_HIT, K_SPHERE, K_SPHERE_MOVING, K_SPHERE_PRECISE, K_SPHERE_HIT,
+               K_QUAD, K_QUAD_HIT, K_XFORM_ENTER, K_MEDIUM, K_MEDIUM_HIT, K_LAMBERTIAN, K_METAL, K_DIELECTRIC, K_ISOTROPIC,
+               K_LIGHT, K_TEX_NOISE, K_TEX_IMAGE, K_TEX_CHECKER, K_FINALIZE_XFORM, K_VOTES, K_LANE_OPS, K_NUM };
+const char* const kCounterNames =
+    "paths,segments,slab,box,box_hit,sphere,sphere_moving,sphere_precise,sphere_hit,quad,quad_hit,xform_enter,medium,"
+    "medium_hit,lambertian,metal,dielectric,isotropic,light,tex_noise,tex_image,tex_checker,finalize_xform,votes,lane_ops";
 
 __device__ __forceinline__ void red_add_f4(float4* addr, float x, float y, float z, float w) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
@@ -77,7 +91,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
     bool active = false;
     Ray ray;
     float3 L, T;
-    int depth = 0, origin_op = -1, pix = 0;
+    int depth = 0, origin = -1, pix = 0;
     uint4 key;
     unsigned long long n_paths = 0, n_segments = 0;
 
@@ -115,7 +129,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
                     L = f3(0.0f, 0.0f, 0.0f);
                     T = f3(1.0f, 1.0f, 1.0f);
                     depth = 0;
-                    origin_op = -1;
+                    origin = -1;
                     active = true;
                     ++n_paths;
                 }
@@ -130,8 +144,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
             // one bounce of ray_color (renderer.rs:139-155), iteratively
             ++n_segments;
             Best best;
-            best.t = __int_as_float(0x7f800000); best.op = -1; best.xf = -1;
-            traverse<true>(S, 0, S.n_words, ray, 0.001f, best, origin_op, key, (uint32_t)depth);
+            traverse<true>(S, 0, S.n_words, ray, 0.001f, __int_as_float(0x7f800000), best, origin, key, (uint32_t)depth);
             bool alive;
             if (best.op < 0) {
                 L = L + T * C.background;                                            // renderer.rs:152-153
@@ -139,9 +152,8 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
             } else {
                 HitRec h;
                 finalize_hit(S, ray, best, h);
-                const uint32_t kind = (uint32_t)fbits(__ldg(S.ops + best.op).w) & 15u;
                 alive = shade(S, P, ray, h, key, (uint32_t)depth, L, T);
-                origin_op = (kind == OP_MEDIUM) ? -1 : best.op;
+                origin = h.origin;
                 ++depth;
                 if (depth >= C.max_depth) alive = false;                             // depth <= 0 returns black (:140-142)
             }
@@ -162,6 +174,9 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
     }
 }
 
+#include "render_v2.cuh"
+#include "render_v3.cuh"
+
 struct DevRayIn { float ox, oy, oz, dx, dy, dz, time, pad; };
 struct DevHitOut { float t, px, py, pz, nx, ny, nz, u, v; int hit, front_face, prim, mat; };
 
@@ -172,9 +187,8 @@ __global__ void hit_kernel(DevScene S, const DevRayIn* rays, int64_t n, float tm
     Ray ray;
     ray.o = f3(r.ox, r.oy, r.oz); ray.d = f3(r.dx, r.dy, r.dz); ray.time = r.time;
     Best best;
-    best.t = tmax; best.op = -1; best.xf = -1;
     const uint4 key = path_key(seed, (uint32_t)k, 0u);
-    traverse<true>(S, 0, S.n_words, ray, tmin, best, -1, key, 0u);
+    traverse<true>(S, 0, S.n_words, ray, tmin, tmax, best, -1, key, 0u);
     DevHitOut o;
     memset(&o, 0, sizeof(o));
     o.prim = -1; o.mat = -1;
@@ -199,11 +213,8 @@ __global__ void texture_kernel(DevScene S, int tex, const float* uvp, int64_t n,
     PerlinShared P{sh_vec, sh_perm};
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    HitRec h;
-    h.u = uvp[k * 5]; h.v = uvp[k * 5 + 1];
-    h.p = f3(uvp[k * 5 + 2], uvp[k * 5 + 3], uvp[k * 5 + 4]);
-    h.uv_lazy = false;
-    const float3 c = texture_value(S, P, tex, h);
+    const float3 c = texture_value(S, P, tex, f3(uvp[k * 5 + 2], uvp[k * 5 + 3], uvp[k * 5 + 4]), uvp[k * 5], uvp[k * 5 + 1], false,
+                                   f3(0.0f, 0.0f, 0.0f));
     rgb[k * 3] = c.x; rgb[k * 3 + 1] = c.y; rgb[k * 3 + 2] = c.z;
 }
 
@@ -282,12 +293,39 @@ DevCamera make_dev_camera(const rt_camera_desc& c) {
 
 }  // namespace
 
+typedef void (*render_fn)(const RenderParams);
+static render_fn v2_kernel(bool counting, int min_blocks) {
+    if (counting) return render_kernel_v2<true, 1>;
+    switch (min_blocks) {
+        case 8: return render_kernel_v2<false, 8>;
+        case 6: return render_kernel_v2<false, 6>;
+        case 5: return render_kernel_v2<false, 5>;
+        default: return render_kernel_v2<false, 4>;
+    }
+}
+
+static render_fn v3_kernel(bool counting, int min_blocks) {
+    if (counting) return render_kernel_v3<true, 1>;
+    switch (min_blocks) {
+        case 8: return render_kernel_v3<false, 8>;
+        case 6: return render_kernel_v3<false, 6>;
+        case 5: return render_kernel_v3<false, 5>;
+        default: return render_kernel_v3<false, 4>;
+    }
+}
+
 struct rt_context {
     int device = 0;
     int sm_count = 0;
     int clock_khz = 0;
     size_t total_mem = 0;
-    int blocks_per_sm = 1;
+    int blocks_per_sm = 1;       // of the selected production kernel
+    int variant = 3;             // 3: render_v3.cuh (product); 2: render_v2.cuh; 1: one-segment-per-iteration loop (A/B only)
+    int min_blocks = 5;          // occupancy variant: resident 128-thread blocks per SM the kernel is compiled for
+    bool hoist_media = true;
+    int shade_min = 24;
+    int slab_fast = 14, slab_reps = 8, sphere_reps = 2;
+    bool box_primitives = true;
     unsigned int* d_counter = nullptr;
     unsigned long long* d_stats = nullptr;
     float4* d_fb = nullptr;
@@ -321,13 +359,32 @@ int rt_context_create(int device_id, rt_context** out) {
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
     c->clock_khz = khz;
+    // development switches (A/B runs; the defaults are the product)
+    if (const char* e = std::getenv("RT_B200_KERNEL")) { const int v = std::atoi(e); c->variant = v == 1 ? 1 : v == 2 ? 2 : 3; }
+    if (const char* e = std::getenv("RT_B200_SHADE_MIN")) c->shade_min = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_SLAB_FAST")) c->slab_fast = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_SLAB_REPS")) c->slab_reps = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_SPHERE_REPS")) c->sphere_reps = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_NO_BOX")) c->box_primitives = std::atoi(e) == 0;
+    if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
+    if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 6 ? 6 : v >= 5 ? 5 : 4; }
     CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
+    CU(cudaFuncSetAttribute(v2_kernel(false, 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
+    CU(cudaFuncSetAttribute(v2_kernel(false, 5), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
+    CU(cudaFuncSetAttribute(v2_kernel(false, 6), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
+    CU(cudaFuncSetAttribute(v2_kernel(false, 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
+    CU(cudaFuncSetAttribute(v2_kernel(true, 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
+    for (int mb : {4, 5, 6, 8})
+        CU(cudaFuncSetAttribute(v3_kernel(false, mb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
+    CU(cudaFuncSetAttribute(v3_kernel(true, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     int bps = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_kernel, kBlockThreads, perlin_smem_bytes()));
+    if (c->variant == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_kernel, kBlockThreads, perlin_smem_bytes()));
+    else if (c->variant == 2) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v2_kernel(false, c->min_blocks), kBlockThreads, perlin_smem_bytes()));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v3_kernel(false, c->min_blocks), kBlockThreads, v3_smem_bytes(1)));
     c->blocks_per_sm = bps > 0 ? bps : 1;
     CU(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_stats, 2 * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_stats, 0, 2 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_stats, K_NUM * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_stats, 0, K_NUM * sizeof(unsigned long long)));
     *out = c;
     return RT_OK;
 }
@@ -364,7 +421,10 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     rt_scene* s = new rt_scene;
     s->ctx = c;
     const char* err = nullptr;
-    int rc = compile_scene(desc, &s->compiled, &err);
+    CompileOptions copt;
+    copt.box_primitives = c->box_primitives;
+    copt.hoist_media = c->hoist_media;
+    int rc = compile_scene(desc, copt, &s->compiled, &err);
     if (rc < 0) { delete s; return fail(rc, err ? err : "compile_scene failed"); }
     if (s->compiled.n_perlin > kMaxPerlinShared) { delete s; return fail(RT_ERR_UNSUPPORTED, "more than 4 NoiseTexture tables in one scene"); }
     const CompiledScene& cs = s->compiled;
@@ -380,7 +440,9 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     UP(cs.perlin_perm, perlin_perm, const uint8_t*)
     UP(cs.precise, precise, const double4*)
 #undef UP
-    s->dev.n_words = (int)cs.ops.size();
+    s->dev.n_words = cs.n_world_words;
+    s->dev.n_media = (int)cs.hoisted_media.size();
+    for (int k = 0; k < s->dev.n_media; ++k) s->dev.media_op[k] = cs.hoisted_media[k];
     s->dev.n_perlin = cs.n_perlin;
     // images: upload RGB8, expand on the device to linear float4 through a 256-entry LUT computed in f64
     std::vector<DevImage> imgs((size_t)desc->n_images);
@@ -427,17 +489,8 @@ void rt_scene_destroy(rt_scene* s) {
     delete s;
 }
 
-int rt_render_accumulate(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
-                         int64_t sample_count, uint64_t seed, void* d_sum_rgba, void* stream_) {
-    if (!c || !s || !cam || !d_sum_rgba) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: null argument");
-    if (sample_count < 0 || sample_count > 0x7fffffff) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: bad sample_count");
-    if (cam->image_width <= 0 || cam->image_height <= 0 || cam->image_width * cam->image_height > 0x7fffffff)
-        return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: bad image size");
-    if (sample_count == 0) return RT_OK;
-    if (cam->max_depth <= 0)   // ray_color returns black at depth <= 0 (renderer.rs:140-142); the CLI scenes never ask for it
-        return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: max_depth must be positive");
-    CU(cudaSetDevice(c->device));
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
+                         int64_t sample_count, uint64_t seed, void* d_sum_rgba, cudaStream_t stream, bool counting) {
     RenderParams prm;
     prm.scene = s->dev;
     prm.cam = make_dev_camera(*cam);
@@ -457,13 +510,70 @@ int rt_render_accumulate(rt_context* c, const rt_scene* s, const rt_camera_desc*
     prm.sum = static_cast<float4*>(d_sum_rgba);
     prm.work_counter = c->d_counter;
     prm.stats = c->d_stats;
+    prm.first_class = (int)s->compiled.first_class;
+    prm.shade_min = c->shade_min;
+    prm.slab_fast = c->slab_fast;
+    prm.slab_reps = c->slab_reps;
+    prm.sphere_reps = c->sphere_reps;
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), stream));
-    CU(cudaMemsetAsync(c->d_stats, 0, 2 * sizeof(unsigned long long), stream));
-    const int grid = c->sm_count * c->blocks_per_sm;
-    render_kernel<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
+    CU(cudaMemsetAsync(c->d_stats, 0, K_NUM * sizeof(unsigned long long), stream));
+    int grid = c->sm_count * c->blocks_per_sm;
+    if (counting || c->variant == 3) {
+        const size_t smem = v3_smem_bytes(s->dev.n_perlin);
+        render_fn fn = v3_kernel(counting, c->min_blocks);
+        int bps = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, kBlockThreads, smem));
+        grid = c->sm_count * (bps > 0 ? bps : 1);
+        fn<<<grid, kBlockThreads, smem, stream>>>(prm);
+    } else if (c->variant == 1) {
+        render_kernel<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
+    } else {
+        v2_kernel(false, c->min_blocks)<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
+    }
     CU(cudaGetLastError());
     c->launches += 1;
     return RT_OK;
+}
+
+static int check_render_args(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_count, const void* buf,
+                             const char* who) {
+    if (!c || !s || !cam || !buf) return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": null argument");
+    if (sample_count < 0 || sample_count > 0x7fffffff) return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": bad sample_count");
+    if (cam->image_width <= 0 || cam->image_height <= 0 || cam->image_width * cam->image_height > 0x7fffffff)
+        return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": bad image size");
+    if (cam->max_depth <= 0)   // ray_color returns black at depth <= 0 (renderer.rs:140-142); the CLI scenes never ask for it
+        return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": max_depth must be positive");
+    return RT_OK;
+}
+
+int rt_render_accumulate(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
+                         int64_t sample_count, uint64_t seed, void* d_sum_rgba, void* stream_) {
+    int rc = check_render_args(c, s, cam, sample_count, d_sum_rgba, "rt_render_accumulate");
+    if (rc < 0) return rc;
+    if (sample_count == 0) return RT_OK;
+    CU(cudaSetDevice(c->device));
+    return launch_render(c, s, cam, sample_begin, sample_count, seed, d_sum_rgba, static_cast<cudaStream_t>(stream_), false);
+}
+
+int rt_render_count_ops(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin, int64_t sample_count,
+                        uint64_t seed, uint64_t* counters, int capacity, const char** names_csv) {
+    int rc = check_render_args(c, s, cam, sample_count, counters, "rt_render_count_ops");
+    if (rc < 0) return rc;
+    if (capacity < (int)K_NUM) return fail(RT_ERR_OUT_OF_RANGE, "rt_render_count_ops: capacity too small");
+    if (names_csv) *names_csv = kCounterNames;
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)cam->image_width * (size_t)cam->image_height;
+    float4* scratch = nullptr;
+    CU(cudaMalloc(&scratch, n * sizeof(float4)));
+    cudaMemset(scratch, 0, n * sizeof(float4));
+    rc = sample_count > 0 ? launch_render(c, s, cam, sample_begin, sample_count, seed, scratch, nullptr, true) : RT_OK;
+    unsigned long long h[K_NUM] = {0};
+    cudaError_t e = cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(scratch);
+    if (rc < 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "rt_render_count_ops");
+    for (int k = 0; k < (int)K_NUM; ++k) counters[k] = h[k];
+    return (int)K_NUM;
 }
 
 int rt_render_get_stats(rt_context* c, rt_render_stats* out) {

@@ -25,7 +25,9 @@ struct DevImage {
 
 struct DevScene {
     const float4* ops;
-    int n_words;
+    int n_words;              // end of the world program (hoisted media bodies live beyond it)
+    int n_media;              // hoisted media, evaluated at the start of every segment
+    int media_op[kMaxHoistedMedia];
     const float4* mats;
     const float4* texs;
     const float4* perlin_vec;
@@ -101,19 +103,43 @@ struct Best {
     int xf;   // word index of the enclosing OP_XFORM_ENTER, -1 = world space
 };
 
-__device__ __forceinline__ bool slab(float4 w0, float4 w1, float3 o, float3 inv, float tmin, float tmax) {
-    // AABB::hit (aabb.rs:64-84) as a tight slab test with the reciprocal hoisted per ray (permitted
-    // substitution, SURVEY.md §8(a)-Q: it only culls more, it never changes which hits exist).
-    const float tx0 = (w0.x - o.x) * inv.x, tx1 = (w1.x - o.x) * inv.x;
-    const float ty0 = (w0.y - o.y) * inv.y, ty1 = (w1.y - o.y) * inv.y;
-    const float tz0 = (w0.z - o.z) * inv.z, tz1 = (w1.z - o.z) * inv.z;
-    // fminf/fmaxf drop a NaN operand (0*inf when the origin lies on a slab of a parallel ray), like f64::min/max
-    const float t_enter = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-    const float t_exit = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-    return t_enter <= t_exit * 1.0000012f + 1e-30f || t_enter <= t_exit;
-}
+// Per-lane traversal cursor over the threaded op stream.
+struct Trav {
+    float3 o, d, inv;   // current (possibly instance-local) ray and its reciprocal direction
+    float3 so, sd;      // outer ray while inside an instance
+    int cur_xf;         // word index of the active OP_XFORM_ENTER, -1 = none
+    int i;              // word index of the next op
+    Best best;
+};
+
+// origin code of a ray that starts on a surface: (op word index << 3) | box face; -1 = none.
+__device__ __forceinline__ int origin_code(int op, int face) { return (op << 3) | face; }
 
 __device__ __forceinline__ float3 safe_inv(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+
+// Entry / exit parameters of the ray against the box {w0.xyz, w1.xyz}, not clamped to any interval.
+// Near/far planes are chosen by the sign of the reciprocal direction (as aabb.rs:73-75 swaps on inv_d < 0), and
+// fminf/fmaxf drop a NaN operand like f64::min/max do: a 0*inf product (origin exactly on a slab plane of a ray
+// parallel to it) leaves that axis unconstrained, which is what the reference computes.
+__device__ __forceinline__ void slab_interval(float4 w0, float4 w1, float3 o, float3 inv, float* t_enter, float* t_exit) {
+    const float ax = (w0.x - o.x) * inv.x, bx = (w1.x - o.x) * inv.x;
+    const float ay = (w0.y - o.y) * inv.y, by = (w1.y - o.y) * inv.y;
+    const float az = (w0.z - o.z) * inv.z, bz = (w1.z - o.z) * inv.z;
+    const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+    *t_enter = fmaxf(fmaxf(sx ? bx : ax, sy ? by : ay), sz ? bz : az);
+    *t_exit = fminf(fminf(sx ? ax : bx, sy ? ay : by), sz ? az : bz);
+}
+
+// AABB::hit (aabb.rs:64-84) as a tight slab test with the reciprocal hoisted per ray (permitted
+// substitution, SURVEY.md §8(a)-Q: it only culls more, it never changes which hits exist). The exit
+// side is inflated by a few ulp so f32 rounding can never cull a box the ray grazes.
+__device__ __forceinline__ bool slab(float4 w0, float4 w1, float3 o, float3 inv, float tmin, float tmax) {
+    float te, tx;
+    slab_interval(w0, w1, o, inv, &te, &tx);
+    te = fmaxf(te, tmin);
+    tx = fminf(tx, tmax);
+    return te <= tx * 1.0000012f + 1e-30f || te <= tx;
+}
 
 // local = R(x - a) + b with R = rotate-y as in hittable.rs:164-168
 __device__ __forceinline__ float3 xform_point(float3 x, float4 w2, float4 w3) {
@@ -131,8 +157,8 @@ __device__ __forceinline__ float3 xform_dir_back(float3 v, float4 w2, float4 w3)
     return f3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z);
 }
 
-// Sphere::hit roots (sphere.rs:59-83). Returns false on a miss; t receives the accepted root.
-// `self_origin`: the ray starts on this very sphere, so the root that is analytically 0 is dropped
+// Sphere::hit roots (sphere.rs:59-83): false on a negative discriminant, else near/far roots.
+// `self_origin`: the ray starts on this very sphere, so the root that is analytically 0 is dropped (NaN)
 // (in f64 the reference rejects it through ray_t.min = 0.001; in f32 its rounding noise can exceed that).
 __device__ __forceinline__ bool sphere_roots_f32(float3 oc, float3 d, float r, bool self_origin, float* r1, float* r2) {
     const float a = dot(d, d);
@@ -144,22 +170,23 @@ __device__ __forceinline__ bool sphere_roots_f32(float3 oc, float3 d, float r, b
     if (disc < 0.0f) return false;
     const float sq = sqrtf(disc * a);
     const float cc = fmaf(-r, r, dot(oc, oc));
+    const float nan = __int_as_float(0x7fc00000);
     float near_root, far_root;
     if (hb > 0.0f) {            // both roots via q to avoid -hb + sq cancellation
         const float q = -hb - sq;
         near_root = q * inv_a;
-        far_root = self_origin ? __int_as_float(0x7fc00000) : cc / q;
+        far_root = self_origin ? nan : cc / q;
     } else {
         const float q = -hb + sq;
         far_root = q * inv_a;
-        near_root = self_origin ? __int_as_float(0x7fc00000) : cc / q;
+        near_root = self_origin ? nan : cc / q;
     }
     *r1 = near_root;
     *r2 = far_root;
     return true;
 }
-__device__ __forceinline__ bool sphere_roots_f64(float3 o, float3 d, float time, const double4* pr, bool moving,
-                                                 bool self_origin, float* r1, float* r2) {
+__device__ __noinline__ bool sphere_roots_f64(float3 o, float3 d, float time, const double4* pr, bool moving,
+                                              bool self_origin, float* r1, float* r2) {
     const double4 c = pr[0];
     double cx = c.x, cy = c.y, cz = c.z;
     if (moving) { const double4 v = pr[1]; cx += v.x * (double)time; cy += v.y * (double)time; cz += v.z * (double)time; }
@@ -172,133 +199,240 @@ __device__ __forceinline__ bool sphere_roots_f64(float3 o, float3 d, float time,
     if (disc < 0.0) return false;
     const double sq = sqrt(disc);
     double n = (-hb - sq) / a, f = (-hb + sq) / a;
-    if (self_origin) { if (hb > 0.0) f = __longlong_as_double(0x7ff8000000000000ll); else n = __longlong_as_double(0x7ff8000000000000ll); }
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (self_origin) { if (hb > 0.0) f = nan; else n = nan; }
     *r1 = (float)n;
     *r2 = (float)f;
     return true;
 }
 
+// ---- one op each; every function advances T.i past the op (or along its skip link) ----
+
+__device__ __forceinline__ void op_inner(Trav& T, float4 w0, float4 w1, float tmin) {
+    T.i = slab(w0, w1, T.o, T.inv, tmin, T.best.t) ? T.i + 2 : fbits(w1.w);
+}
+
+__device__ __forceinline__ void op_sphere(const DevScene& S, Trav& T, float4 w0, float4 w1, float time, float tmin, int origin) {
+    const uint32_t flags = ((uint32_t)fbits(w0.w) >> 4) & 15u;
+    const bool moving = flags & FLAG_MOVING;
+    const bool self_origin = (origin >> 3) == T.i && origin >= 0;
+    float r1, r2;
+    bool ok;
+    if (flags & FLAG_PRECISE) {
+        ok = sphere_roots_f64(T.o, T.d, time, S.precise + 2 * fbits(w1.w), moving, self_origin, &r1, &r2);
+    } else {
+        float3 c = f3(w0);
+        if (moving) c = fma3(time, f3(__ldg(S.ops + T.i + 2)), c);  // sphere.rs:53-55
+        ok = sphere_roots_f32(T.o - c, T.d, w1.x, self_origin, &r1, &r2);
+    }
+    if (ok) {
+        float root = r1;  // ray_t.surrounds: open interval (sphere.rs:78-83)
+        if (!(tmin < root && root < T.best.t)) root = r2;
+        if (tmin < root && root < T.best.t) { T.best.t = root; T.best.op = T.i; T.best.xf = T.cur_xf; }
+    }
+    T.i += moving ? 3 : 2;
+}
+
+__device__ __forceinline__ void op_quad(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin, int origin) {
+    const float3 n = f3(w0);
+    const float denom = dot(n, T.d);
+    const float4 w3 = __ldg(S.ops + T.i + 3);
+    const bool self_origin = (origin >> 3) == T.i && origin >= 0;    // a ray cannot re-hit the plane it starts on
+    if (!(fabsf(denom) < 1e-8f) && !self_origin) {                   // quad.rs:110-112
+        const float t = (w3.x - dot(n, T.o)) / denom;
+        if (tmin <= t && t <= T.best.t) {                             // ray_t.contains: closed (quad.rs:115)
+            const float4 w2 = __ldg(S.ops + T.i + 2);
+            const float3 p = fma3(t, T.d, T.o);
+            const float alpha = dot(f3(w1), p) + w1.w;
+            const float beta = dot(f3(w2), p) + w2.w;
+            if (!(alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f)) { T.best.t = t; T.best.op = T.i; T.best.xf = T.cur_xf; }
+        }
+    }
+    T.i += 4;
+}
+
+// Quad::cube's six quads (quad.rs:45-93) as one slab test: the nearest face hit inside [tmin, best.t] is the
+// entry plane if it lies in the interval, else the exit plane (HittableList::hit keeps the closest, closed interval).
+__device__ __forceinline__ void op_box(Trav& T, float4 w0, float4 w1, float tmin, int origin) {
+    float te, tx;
+    slab_interval(w0, w1, T.o, T.inv, &te, &tx);
+    if (te <= tx) {
+        if ((origin >> 3) == T.i && origin >= 0) {   // ray starts on a face of this box: that plane cannot be hit again
+            const int face = origin & 7;             // 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y
+            const int axis = (face == 1 || face == 3) ? 0 : (face >= 4 ? 1 : 2);
+            const bool max_side = face == 0 || face == 1 || face == 4;
+            const float plane = axis == 0 ? (max_side ? w1.x : w0.x) : axis == 1 ? (max_side ? w1.y : w0.y) : (max_side ? w1.z : w0.z);
+            const float oa = axis == 0 ? T.o.x : axis == 1 ? T.o.y : T.o.z;
+            const float ia = axis == 0 ? T.inv.x : axis == 1 ? T.inv.y : T.inv.z;
+            const float t_self = (plane - oa) * ia;
+            const float nan = __int_as_float(0x7fc00000);
+            if (te == t_self) te = nan;
+            if (tx == t_self) tx = nan;
+        }
+        float t = te;
+        if (!(tmin <= t && t <= T.best.t)) t = tx;
+        if (tmin <= t && t <= T.best.t) { T.best.t = t; T.best.op = T.i; T.best.xf = T.cur_xf; }
+    }
+    T.i += 3;
+}
+
+__device__ __forceinline__ void op_xform_enter(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin) {
+    if (slab(w0, w1, T.o, T.inv, tmin, T.best.t)) {
+        const float4 w2 = __ldg(S.ops + T.i + 2), w3 = __ldg(S.ops + T.i + 3);
+        T.so = T.o; T.sd = T.d;
+        T.o = xform_point(T.o, w2, w3);     // hittable.rs:98,164-168
+        T.d = xform_dir(T.d, w2, w3);
+        T.inv = safe_inv(T.d);
+        T.cur_xf = T.i;
+        T.i += 4;
+    } else {
+        T.i = fbits(w1.w);
+    }
+}
+
+__device__ __forceinline__ void op_xform_exit(Trav& T) {
+    T.o = T.so; T.d = T.sd;
+    T.inv = safe_inv(T.d);
+    T.cur_xf = -1;
+    T.i += 2;
+}
+
+// INNER / BOX / XFORM_ENTER / XFORM_EXIT in one body that shares the slab arithmetic (the render kernel's
+// "slab class"). Returns the class of the lane's next op, read from the header's successor bits.
+__device__ __forceinline__ uint32_t op_slab_class(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin, int origin) {
+    const uint32_t hdr = (uint32_t)fbits(w0.w);
+    const uint32_t kind = hdr & 15u;
+    const uint32_t ft = (hdr >> 8) & 7u, sk = (hdr >> 11) & 7u;
+    if (kind == OP_XFORM_EXIT) { op_xform_exit(T); return ft; }
+    float te, tx;
+    slab_interval(w0, w1, T.o, T.inv, &te, &tx);
+    if (kind == OP_BOX) {
+        if ((origin >> 3) == T.i && origin >= 0) {   // rare: the ray starts on a face of this box
+            op_box(T, w0, w1, tmin, origin);
+            return ft;
+        }
+        float t = te;
+        if (!(tmin <= t && t <= T.best.t)) t = tx;
+        if (te <= tx && tmin <= t && t <= T.best.t) { T.best.t = t; T.best.op = T.i; T.best.xf = T.cur_xf; }
+        T.i += 3;
+        return ft;
+    }
+    const float ce = fmaxf(te, tmin), cx = fminf(tx, T.best.t);
+    const bool hit = ce <= cx * 1.0000012f + 1e-30f || ce <= cx;
+    if (!hit) { T.i = fbits(w1.w); return sk; }
+    if (kind == OP_INNER) { T.i += 2; return ft; }
+    const float4 w2 = __ldg(S.ops + T.i + 2), w3 = __ldg(S.ops + T.i + 3);   // OP_XFORM_ENTER
+    T.so = T.o; T.sd = T.d;
+    T.o = xform_point(T.o, w2, w3);
+    T.d = xform_dir(T.d, w2, w3);
+    T.inv = safe_inv(T.d);
+    T.cur_xf = T.i;
+    T.i += 4;
+    return ft;
+}
+
+__device__ float boundary_closest_t(const DevScene& S, int begin, int end, const Ray& ray, float tmin, float tmax);
+
+// ConstantMedium::hit (constant_medium.rs:34-70); the medium's box was tested by the preceding OP_INNER.
+__device__ __forceinline__ void op_medium(const DevScene& S, Trav& T, float4 w0, float4 w1, float time, float tmin,
+                                          uint4 key, uint32_t seg) {
+    const int bkind = (int)(((uint32_t)fbits(w0.w) >> 4) & 15u);
+    const float4 w2 = __ldg(S.ops + T.i + 2);
+    float t1, t2;
+    bool ok;
+    int next;
+    if (bkind == MEDIUM_BOUNDARY_SPHERE) {
+        const uint32_t aux = (uint32_t)fbits(w2.w);
+        const bool moving = (aux >> 24) & FLAG_MOVING;
+        if ((aux >> 24) & FLAG_PRECISE) {
+            ok = sphere_roots_f64(T.o, T.d, time, S.precise + 2 * (aux & 0xffffffu), moving, false, &t1, &t2);
+        } else {
+            float3 c = f3(w1);
+            if (moving) c = fma3(time, f3(w2), c);
+            ok = sphere_roots_f32(T.o - c, T.d, w1.w, false, &t1, &t2);
+        }
+        // hit1 over the universe takes the near root; hit2 needs a root > hit1.t + 0.0001
+        ok = ok && (t2 > t1 + 0.0001f);
+        next = T.i + 3;
+    } else if (bkind == MEDIUM_BOUNDARY_XBOX) {
+        // both boundary hits of a (rotated, translated) cube from one slab test in the cube's frame
+        const float4 lo = __ldg(S.ops + T.i + 3), hi = __ldg(S.ops + T.i + 4);
+        const float3 lo_ = xform_point(T.o, w1, w2), ld_ = xform_dir(T.d, w1, w2);
+        slab_interval(lo, hi, lo_, safe_inv(ld_), &t1, &t2);
+        const float inf = __int_as_float(0x7f800000);
+        ok = (t1 <= t2) && (t2 >= t1 + 0.0001f) && fabsf(t1) < inf && fabsf(t2) < inf;   // hit2: closed interval from hit1.t + 0.0001
+        next = T.i + 5;
+    } else {
+        Ray lr; lr.o = T.o; lr.d = T.d; lr.time = time;
+        const float inf = __int_as_float(0x7f800000);
+        t1 = boundary_closest_t(S, fbits(w1.x), fbits(w1.y), lr, -inf, inf);
+        ok = (t1 == t1);
+        if (ok) { t2 = boundary_closest_t(S, fbits(w1.x), fbits(w1.y), lr, t1 + 0.0001f, inf); ok = (t2 == t2); }
+        next = fbits(w1.y);
+    }
+    if (ok) {
+        t1 = fmaxf(t1, tmin);
+        t2 = fminf(t2, T.best.t);
+        if (t1 < t2) {
+            t1 = fmaxf(t1, 0.0f);
+            const float ray_length = sqrtf(dot(T.d, T.d));
+            const float inside = (t2 - t1) * ray_length;
+            const float u = u01(draw(key, seg, P_MEDIUM + (uint32_t)fbits(w0.z)).x);
+            const float hit_distance = w0.x * logf(u);   // drawn only on this branch (constant_medium.rs:48)
+            if (hit_distance <= inside) { T.best.t = t1 + hit_distance / ray_length; T.best.op = T.i; T.best.xf = T.cur_xf; }
+        }
+    }
+    T.i = next;
+}
+
+__device__ __forceinline__ void trav_begin(Trav& T, const Ray& ray, int begin, float tmax) {
+    T.o = ray.o; T.d = ray.d;
+    T.inv = safe_inv(ray.d);
+    T.so = ray.o; T.sd = ray.d;
+    T.cur_xf = -1;
+    T.i = begin;
+    T.best.t = tmax; T.best.op = -1; T.best.xf = -1;
+}
+
+// Hoisted (world-space) media: evaluated before the traversal of every segment; each may lower best.t.
+__device__ __forceinline__ void media_prepass(const DevScene& S, Trav& T, float time, float tmin, uint4 key, uint32_t seg) {
+    const int begin = T.i;
+    for (int m = 0; m < S.n_media; ++m) {
+        T.i = S.media_op[m];
+        op_medium(S, T, __ldg(S.ops + T.i), __ldg(S.ops + T.i + 1), time, tmin, key, seg);
+    }
+    T.i = begin;
+}
+
+// Generic loop (parity kernels, medium boundary programs). WORLD = false: t only, no media.
 template <bool WORLD>
-__device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, const Ray& ray, float tmin, Best& best,
-                                         int origin_op, uint4 key, uint32_t seg);
+__device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, const Ray& ray, float tmin, float tmax,
+                                         Best& best, int origin, uint4 key, uint32_t seg) {
+    Trav T;
+    trav_begin(T, ray, begin, tmax);
+    if (WORLD) media_prepass(S, T, ray.time, tmin, key, seg);
+    const float4* __restrict__ ops = S.ops;
+    while (T.i < end) {
+        const float4 w0 = __ldg(ops + T.i);
+        const float4 w1 = __ldg(ops + T.i + 1);
+        const uint32_t kind = (uint32_t)fbits(w0.w) & 15u;
+        if (kind == OP_INNER) op_inner(T, w0, w1, tmin);
+        else if (kind == OP_SPHERE) op_sphere(S, T, w0, w1, ray.time, tmin, origin);
+        else if (kind == OP_BOX) op_box(T, w0, w1, tmin, origin);
+        else if (kind == OP_QUAD) op_quad(S, T, w0, w1, tmin, origin);
+        else if (kind == OP_XFORM_ENTER) op_xform_enter(S, T, w0, w1, tmin);
+        else if (kind == OP_XFORM_EXIT) op_xform_exit(T);
+        else if (WORLD) op_medium(S, T, w0, w1, ray.time, tmin, key, seg);
+        else T.i = end;   // a medium inside a boundary program is rejected at upload
+    }
+    best = T.best;
+}
 
 // Closest t of a medium's boundary program (t only; constant_medium.rs:35-39 needs nothing else).
 __device__ __noinline__ float boundary_closest_t(const DevScene& S, int begin, int end, const Ray& ray, float tmin, float tmax) {
     Best b;
-    b.t = tmax; b.op = -1; b.xf = -1;
-    traverse<false>(S, begin, end, ray, tmin, b, -1, make_uint4(0, 0, 0, 0), 0u);
+    traverse<false>(S, begin, end, ray, tmin, tmax, b, -1, make_uint4(0, 0, 0, 0), 0u);
     return b.op >= 0 ? b.t : __int_as_float(0x7fc00000);
-}
-
-template <bool WORLD>
-__device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, const Ray& ray, float tmin, Best& best,
-                                         int origin_op, uint4 key, uint32_t seg) {
-    float3 o = ray.o, d = ray.d;
-    float3 inv = safe_inv(d);
-    float3 so = o, sd = d;  // outer ray while inside an instance
-    int cur_xf = -1;
-    int i = begin;
-    const float4* __restrict__ ops = S.ops;
-    while (i < end) {
-        const float4 w0 = __ldg(ops + i);
-        const float4 w1 = __ldg(ops + i + 1);
-        const uint32_t hdr = (uint32_t)fbits(w0.w);
-        const uint32_t kind = hdr & 15u;
-        if (kind == OP_INNER) {
-            i = slab(w0, w1, o, inv, tmin, best.t) ? i + 2 : fbits(w1.w);
-        } else if (kind == OP_SPHERE) {
-            const uint32_t flags = (hdr >> 4) & 15u;
-            const bool moving = flags & FLAG_MOVING;
-            float r1, r2;
-            bool ok;
-            if (flags & FLAG_PRECISE) {
-                ok = sphere_roots_f64(o, d, ray.time, S.precise + 2 * fbits(w1.w), moving, i == origin_op, &r1, &r2);
-            } else {
-                float3 c = f3(w0);
-                if (moving) c = fma3(ray.time, f3(__ldg(ops + i + 2)), c);  // sphere.rs:53-55
-                ok = sphere_roots_f32(o - c, d, w1.x, i == origin_op, &r1, &r2);
-            }
-            if (ok) {
-                float root = r1;  // ray_t.surrounds: open interval (sphere.rs:78-83)
-                if (!(tmin < root && root < best.t)) root = r2;
-                if (tmin < root && root < best.t) { best.t = root; best.op = i; best.xf = cur_xf; }
-            }
-            i += moving ? 3 : 2;
-        } else if (kind == OP_QUAD) {
-            const float3 n = f3(w0);
-            const float denom = dot(n, d);
-            const float4 w3 = __ldg(ops + i + 3);
-            if (!(fabsf(denom) < 1e-8f) && i != origin_op) {       // quad.rs:110-112
-                const float t = (w3.x - dot(n, o)) / denom;
-                if (tmin <= t && t <= best.t) {                      // ray_t.contains: closed (quad.rs:115)
-                    const float4 w2 = __ldg(ops + i + 2);
-                    const float3 p = fma3(t, d, o);
-                    const float alpha = dot(f3(w1), p) + w1.w;
-                    const float beta = dot(f3(w2), p) + w2.w;
-                    if (!(alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f)) { best.t = t; best.op = i; best.xf = cur_xf; }
-                }
-            }
-            i += 4;
-        } else if (kind == OP_XFORM_ENTER) {
-            if (slab(w0, w1, o, inv, tmin, best.t)) {
-                const float4 w2 = __ldg(ops + i + 2), w3 = __ldg(ops + i + 3);
-                so = o; sd = d;
-                o = xform_point(o, w2, w3);     // hittable.rs:98,164-168
-                d = xform_dir(d, w2, w3);
-                inv = safe_inv(d);
-                cur_xf = i;
-                i += 4;
-            } else {
-                i = fbits(w1.w);
-            }
-        } else if (kind == OP_XFORM_EXIT) {
-            o = so; d = sd;
-            inv = safe_inv(d);
-            cur_xf = -1;
-            i += 2;
-        } else {  // OP_MEDIUM — constant_medium.rs:34-70
-            const int skip = fbits(w1.w);
-            if (WORLD && slab(w0, w1, o, inv, tmin, best.t)) {
-                const float4 w2 = __ldg(ops + i + 2);
-                const float4 w3 = __ldg(ops + i + 3);
-                float t1, t2;
-                bool ok;
-                if (fbits(w2.w) == MEDIUM_BOUNDARY_SPHERE) {
-                    const float4 w4 = __ldg(ops + i + 4);
-                    const uint32_t aux = (uint32_t)fbits(w4.w);
-                    const bool moving = (aux >> 24) & FLAG_MOVING;
-                    if ((aux >> 24) & FLAG_PRECISE) {
-                        ok = sphere_roots_f64(o, d, ray.time, S.precise + 2 * (aux & 0xffffffu), moving, false, &t1, &t2);
-                    } else {
-                        float3 c = f3(w3);
-                        if (moving) c = fma3(ray.time, f3(w4), c);
-                        ok = sphere_roots_f32(o - c, d, w3.w, false, &t1, &t2);
-                    }
-                    // hit1 over the universe takes the near root; hit2 needs a root > hit1.t + 0.0001
-                    ok = ok && (t2 > t1 + 0.0001f);
-                } else {
-                    Ray lr; lr.o = o; lr.d = d; lr.time = ray.time;
-                    const float inf = __int_as_float(0x7f800000);
-                    t1 = boundary_closest_t(S, fbits(w3.x), fbits(w3.y), lr, -inf, inf);
-                    ok = (t1 == t1);
-                    if (ok) { t2 = boundary_closest_t(S, fbits(w3.x), fbits(w3.y), lr, t1 + 0.0001f, inf); ok = (t2 == t2); }
-                }
-                if (ok) {
-                    t1 = fmaxf(t1, tmin);
-                    t2 = fminf(t2, best.t);
-                    if (t1 < t2) {
-                        t1 = fmaxf(t1, 0.0f);
-                        const float ray_length = sqrtf(dot(d, d));
-                        const float inside = (t2 - t1) * ray_length;
-                        const float u = u01(draw(key, seg, P_MEDIUM + (uint32_t)fbits(w2.z)).x);
-                        const float hit_distance = w2.x * logf(u);   // drawn only on this branch (constant_medium.rs:48)
-                        if (hit_distance <= inside) { best.t = t1 + hit_distance / ray_length; best.op = i; best.xf = cur_xf; }
-                    }
-                }
-            }
-            i = skip;
-        }
-    }
 }
 
 // ------------------------------------------------------------------ hit record of the winner
@@ -306,6 +440,7 @@ struct HitRec {
     float3 p, normal;
     float t, u, v;
     int mat, prim;
+    int origin;         // origin code for the ray that leaves this hit (-1 for media)
     bool front_face;
     bool uv_lazy;       // sphere: u,v derived from `sn` only if a texture asks (sphere.rs:87 computes it always)
     float3 sn;          // sphere outward normal in the sphere's own space
@@ -317,6 +452,17 @@ __device__ __forceinline__ void sphere_uv(float3 n, float* u, float* v) {   // s
     const float phi = atan2f(-n.z, n.x) + PI;
     *u = phi / (2.0f * PI);
     *v = theta / PI;
+}
+
+// hit point in f64 relative to the centre: keeps the normal of a huge sphere accurate
+__device__ __noinline__ float3 precise_sphere_normal(const double4* pr, bool moving, float3 o, float3 d, float t, float time) {
+    const double4 c = pr[0];
+    double cx = c.x, cy = c.y, cz = c.z;
+    if (moving) { const double4 cv = pr[1]; cx += cv.x * (double)time; cy += cv.y * (double)time; cz += cv.z * (double)time; }
+    const double inv_r = 1.0 / c.w;
+    return f3((float)((((double)o.x - cx) + (double)t * (double)d.x) * inv_r),
+              (float)((((double)o.y - cy) + (double)t * (double)d.y) * inv_r),
+              (float)((((double)o.z - cz) + (double)t * (double)d.z) * inv_r));
 }
 
 __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, const Best& best, HitRec& h) {
@@ -335,19 +481,13 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, 
     h.t = t;
     h.uv_lazy = false;
     h.u = 0.0f; h.v = 0.0f;
+    h.origin = origin_code(best.op, 0);
     float3 outward;
     if (kind == OP_SPHERE) {
         const uint32_t flags = (hdr >> 4) & 15u;
         const float3 pl = fma3(t, d, o);
         if (flags & FLAG_PRECISE) {
-            const double4 c = S.precise[2 * fbits(w1.w)];
-            double cx = c.x, cy = c.y, cz = c.z;
-            if (flags & FLAG_MOVING) { const double4 cv = S.precise[2 * fbits(w1.w) + 1]; cx += cv.x * (double)ray.time; cy += cv.y * (double)ray.time; cz += cv.z * (double)ray.time; }
-            const double inv_r = 1.0 / c.w;
-            // hit point in f64 relative to the centre: keeps the normal of a huge sphere accurate
-            outward = f3((float)((((double)o.x - cx) + (double)t * (double)d.x) * inv_r),
-                         (float)((((double)o.y - cy) + (double)t * (double)d.y) * inv_r),
-                         (float)((((double)o.z - cz) + (double)t * (double)d.z) * inv_r));
+            outward = precise_sphere_normal(S.precise + 2 * fbits(w1.w), flags & FLAG_MOVING, o, d, t, ray.time);
         } else {
             float3 c = f3(w0);
             if (flags & FLAG_MOVING) c = fma3(ray.time, f3(__ldg(ops + best.op + 2)), c);
@@ -365,11 +505,40 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, 
         h.v = dot(f3(w2), pl) + w2.w;
         h.mat = fbits(w3.y);
         h.prim = fbits(w3.z);
+    } else if (kind == OP_BOX) {
+        // which face produced t: the plane whose parameter equals t exactly (t was taken from these very values);
+        // on an edge the face that comes later in the list wins (closed interval, hittable.rs:66-71)
+        const float3 inv = safe_inv(d);
+        const float tx0 = (w0.x - o.x) * inv.x, tx1 = (w1.x - o.x) * inv.x;
+        const float ty0 = (w0.y - o.y) * inv.y, ty1 = (w1.y - o.y) * inv.y;
+        const float tz0 = (w0.z - o.z) * inv.z, tz1 = (w1.z - o.z) * inv.z;
+        int face = 0;
+        if (tz1 == t) face = 0;
+        if (tx1 == t) face = 1;
+        if (tz0 == t) face = 2;
+        if (tx0 == t) face = 3;
+        if (ty1 == t) face = 4;
+        if (ty0 == t) face = 5;
+        const float3 pl = fma3(t, d, o);
+        const float ex = 1.0f / (w1.x - w0.x), ey = 1.0f / (w1.y - w0.y), ez = 1.0f / (w1.z - w0.z);
+        const float ax = (pl.x - w0.x) * ex, ay = (pl.y - w0.y) * ey, az = (pl.z - w0.z) * ez;   // 0..1 along +x,+y,+z
+        outward = f3(0.0f, 0.0f, 0.0f);
+        switch (face) {   // (u, v) = (alpha, beta) of the face's quad (quad.rs:55-90)
+            case 0: outward.z = 1.0f;  h.u = ax;        h.v = ay; break;
+            case 1: outward.x = 1.0f;  h.u = 1.0f - az; h.v = ay; break;
+            case 2: outward.z = -1.0f; h.u = 1.0f - ax; h.v = ay; break;
+            case 3: outward.x = -1.0f; h.u = az;        h.v = ay; break;
+            case 4: outward.y = 1.0f;  h.u = ax;        h.v = 1.0f - az; break;
+            default: outward.y = -1.0f; h.u = ax;       h.v = az; break;
+        }
+        h.mat = fbits(w1.w);
+        h.prim = fbits(__ldg(ops + best.op + 2).x) + face;
+        h.origin = origin_code(best.op, face);
     } else {  // OP_MEDIUM: HitRecord::new(r.at(t), phase, t, r, r.direction) (constant_medium.rs:52-58)
-        const float4 w2 = __ldg(ops + best.op + 2);
         outward = d;
-        h.mat = fbits(w2.y);
-        h.prim = fbits(w2.z);
+        h.mat = fbits(w0.y);
+        h.prim = fbits(w0.z);
+        h.origin = -1;
     }
     h.front_face = dot(d, outward) < 0.0f;                  // hittable.rs:23
     float3 n = h.front_face ? outward : -outward;
@@ -412,7 +581,7 @@ __device__ __forceinline__ float perlin_noise(const PerlinShared& P, int table, 
     return acc;
 }
 
-__device__ __forceinline__ float perlin_turbulence(const PerlinShared& P, int table, float3 p) {   // perlin.rs:52-64, depth 7
+__device__ __noinline__ float perlin_turbulence(const PerlinShared& P, int table, float3 p) {   // perlin.rs:52-64, depth 7
     float acc = 0.0f, w = 1.0f;
 #pragma unroll 1
     for (int o = 0; o < 7; ++o) {
@@ -423,7 +592,10 @@ __device__ __forceinline__ float perlin_turbulence(const PerlinShared& P, int ta
     return fabsf(acc);
 }
 
-__device__ __forceinline__ float3 texture_value(const DevScene& S, const PerlinShared& P, int tex, HitRec& h) {
+// Texture::value (texture.rs:12-14). One out-of-line copy: it is called once per shaded hit, and keeping it (and
+// the Perlin code behind it) out of the render loop's body keeps the loop's instruction footprint small.
+__device__ __noinline__ float3 texture_value(const DevScene& S, const PerlinShared& P, int tex, float3 p, float u, float v,
+                                             bool uv_lazy, float3 sn) {
     const float4* __restrict__ T = S.texs;
     for (int guard = 0; guard < 16; ++guard) {
         const float4 t0 = __ldg(T + 2 * tex);
@@ -431,18 +603,18 @@ __device__ __forceinline__ float3 texture_value(const DevScene& S, const PerlinS
         if (kind == RT_TEX_SOLID) {
             return f3(__ldg(T + 2 * tex + 1));
         } else if (kind == RT_TEX_CHECKER) {   // texture.rs:59-70
-            const int x = (int)floorf(t0.w * h.p.x), y = (int)floorf(t0.w * h.p.y), z = (int)floorf(t0.w * h.p.z);
+            const int x = (int)floorf(t0.w * p.x), y = (int)floorf(t0.w * p.y), z = (int)floorf(t0.w * p.z);
             tex = ((x + y + z) % 2 == 0) ? fbits(t0.y) : fbits(t0.z);
         } else if (kind == RT_TEX_IMAGE) {     // texture.rs:82-93
-            if (h.uv_lazy) { sphere_uv(h.sn, &h.u, &h.v); h.uv_lazy = false; }
+            if (uv_lazy) { sphere_uv(sn, &u, &v); uv_lazy = false; }
             const DevImage im = S.images[fbits(t0.y)];
-            const float u = fminf(fmaxf(h.u, 0.0f), 1.0f);
-            const float v = 1.0f - fminf(fmaxf(h.v, 0.0f), 1.0f);
-            const uint32_t i = (uint32_t)(u * (float)(im.width - 1));
-            const uint32_t j = (uint32_t)(v * (float)(im.height - 1));
+            const float uc = fminf(fmaxf(u, 0.0f), 1.0f);
+            const float vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+            const uint32_t i = (uint32_t)(uc * (float)(im.width - 1));
+            const uint32_t j = (uint32_t)(vc * (float)(im.height - 1));
             return f3(__ldg(im.texels + (size_t)j * im.width + i));
         } else {                                // texture.rs:107-111
-            const float s = sinf(t0.w * h.p.z + 10.0f * perlin_turbulence(P, fbits(t0.y), h.p)) * 0.5f + 0.5f;
+            const float s = sinf(t0.w * p.z + 10.0f * perlin_turbulence(P, fbits(t0.y), p)) * 0.5f + 0.5f;
             return f3(s, s, s);
         }
     }
@@ -452,27 +624,15 @@ __device__ __forceinline__ float3 texture_value(const DevScene& S, const PerlinS
 // ------------------------------------------------------------------ materials
 __device__ __forceinline__ float3 reflect3(float3 v, float3 n) { return v - (2.0f * dot(v, n)) * n; }   // vec3.rs:91-93
 
-// Returns true if the path continues; updates ray and throughput, adds emission to L.
+// Material::emitted + Material::scatter (material.rs:26-138). Returns true if the path continues; updates ray and
+// throughput, adds emission to L. Written with a single texture call site.
 __device__ __forceinline__ bool shade(const DevScene& S, const PerlinShared& P, Ray& ray, HitRec& h, uint4 key, uint32_t seg,
                                       float3& L, float3& T) {
     const float4 m0 = __ldg(S.mats + 2 * h.mat);
     const int kind = fbits(m0.x);
-    if (kind == RT_MAT_DIFFUSE_LIGHT) {   // emitted (both faces) and no scatter: material.rs:114-122
-        L = L + T * texture_value(S, P, fbits(m0.y), h);
-        return false;
-    }
-    const uint4 r = draw(key, seg, P_SCATTER);
-    float3 dir, att;
-    if (kind == RT_MAT_LAMBERTIAN) {      // material.rs:27-41
-        dir = h.normal + unit_vector(u01(r.x), u01(r.y));
-        if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = h.normal;
-        att = texture_value(S, P, fbits(m0.y), h);
-    } else if (kind == RT_MAT_METAL) {    // material.rs:54-63
-        const float3 in_sphere = unit_vector(u01(r.x), u01(r.y)) * cbrtf(u01(r.z));
-        dir = reflect3(normalize3(ray.d), h.normal) + m0.z * in_sphere;
-        if (!(dot(dir, h.normal) > 0.0f)) return false;
-        att = f3(__ldg(S.mats + 2 * h.mat + 1));
-    } else if (kind == RT_MAT_DIELECTRIC) {   // material.rs:81-103
+    float3 dir = h.normal, att = f3(1.0f, 1.0f, 1.0f);
+    bool scattered = true;
+    if (kind == RT_MAT_DIELECTRIC) {          // material.rs:81-103
         const float ratio = h.front_face ? 1.0f / m0.z : m0.z;
         const float3 unit = normalize3(ray.d);
         const float cos_theta = fminf(dot(-unit, h.normal), 1.0f);
@@ -481,18 +641,35 @@ __device__ __forceinline__ bool shade(const DevScene& S, const PerlinShared& P, 
         r0 = r0 * r0;
         const float x = 1.0f - cos_theta;
         const float refl = r0 + (1.0f - r0) * (x * x * x * x * x);           // material.rs:74-78
-        if (ratio * sin_theta > 1.0f || refl > u01(r.w)) {
+        if (ratio * sin_theta > 1.0f || refl > u01(draw(key, seg, P_SCATTER).w)) {
             dir = reflect3(unit, h.normal);
         } else {                                                               // vec3.rs:96-101
             const float3 perp = ratio * (unit + cos_theta * h.normal);
-            const float3 par = (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * h.normal;
-            dir = perp + par;
+            dir = perp + (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * h.normal;
         }
-        att = f3(1.0f, 1.0f, 1.0f);
-    } else {                               // isotropic: material.rs:132-138
-        dir = unit_vector(u01(r.x), u01(r.y));
-        att = texture_value(S, P, fbits(m0.y), h);
+    } else if (kind != RT_MAT_DIFFUSE_LIGHT) {
+        const uint4 r = draw(key, seg, P_SCATTER);
+        const float3 uv = unit_vector(u01(r.x), u01(r.y));
+        if (kind == RT_MAT_METAL) {           // material.rs:54-63
+            dir = reflect3(normalize3(ray.d), h.normal) + (m0.z * cbrtf(u01(r.z))) * uv;
+            scattered = dot(dir, h.normal) > 0.0f;
+            att = f3(__ldg(S.mats + 2 * h.mat + 1));
+        } else if (kind == RT_MAT_LAMBERTIAN) {   // material.rs:27-41
+            dir = h.normal + uv;
+            if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = h.normal;
+        } else {                              // isotropic: material.rs:132-138
+            dir = uv;
+        }
     }
+    if (kind == RT_MAT_LAMBERTIAN || kind == RT_MAT_ISOTROPIC || kind == RT_MAT_DIFFUSE_LIGHT) {
+        const float3 c = texture_value(S, P, fbits(m0.y), h.p, h.u, h.v, h.uv_lazy, h.sn);
+        if (kind == RT_MAT_DIFFUSE_LIGHT) {   // emitted (both faces), no scatter: material.rs:114-122
+            L = L + T * c;
+            return false;
+        }
+        att = c;
+    }
+    if (!scattered) return false;
     T = T * att;
     ray.o = h.p;
     ray.d = dir;

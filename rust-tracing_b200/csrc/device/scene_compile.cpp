@@ -54,6 +54,7 @@ float round_up(double v) {
 struct Compiler {
     const rt_scene_desc* d;
     CompiledScene* out;
+    CompileOptions opt;
     std::string err;
     int status = 0;
     bool in_xform = false;
@@ -61,6 +62,8 @@ struct Compiler {
     std::vector<Box> tight_node;      // memo, by bvh node index
     std::vector<char> have_h, have_n;
     double scale = 1.0;
+    std::vector<F4> hoisted;             // bodies of world-space media (appended after the world program)
+    std::vector<int32_t> hoisted_at;     // offsets into `hoisted`
 
     bool fail(int code, const std::string& m) {
         if (status == 0) { status = code; err = m; }
@@ -176,6 +179,54 @@ struct Compiler {
         push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), 0.0f);
     }
 
+    // A list made by Quad::cube (quad.rs:45-93) whose six quads still are what cube() produced: consecutive ids,
+    // one material, axis-aligned faces of the recorded min/max corners.
+    bool is_cube(int id) const {
+        if (!opt.box_primitives) return false;
+        const rt_hittable_desc& h = d->hittables[id];
+        if (h.kind != RT_HIT_LIST || !(h.flags & RT_FLAG_CUBE_LIST) || h.count != 6) return false;
+        const int first = d->list_items[h.child];
+        for (int k = 0; k < 6; ++k) {
+            const int q = d->list_items[h.child + k];
+            if (q != first + k || q < 0 || q >= d->n_hittables) return false;
+            if (d->hittables[q].kind != RT_HIT_QUAD || d->hittables[q].mat != d->hittables[first].mat) return false;
+        }
+        for (int c = 0; c < 3; ++c) if (!(h.v0[c] < h.v1[c])) return false;   // a degenerate (flat) cube keeps its quads
+        return true;
+    }
+    void emit_box(int id) {
+        const rt_hittable_desc& h = d->hittables[id];
+        const int first = d->list_items[h.child];
+        push((float)h.v0[0], (float)h.v0[1], (float)h.v0[2], bits_to_float(make_hdr(OP_BOX)));
+        push((float)h.v1[0], (float)h.v1[1], (float)h.v1[2], int_to_float_bits(d->hittables[first].mat));
+        push(int_to_float_bits(first), 0.0f, 0.0f, 0.0f);
+        for (int c = 0; c < 3; ++c) scale = std::fmax(scale, std::fmax(std::fabs(h.v0[c]), std::fabs(h.v1[c])));
+    }
+
+    // Fold a chain of directly nested Translate / RotateY wrappers (outermost first) into local = R(x - a) + b.
+    int fold_xform(int id, double a[3], double b[3], double* s, double* c) const {
+        a[0] = a[1] = a[2] = b[0] = b[1] = b[2] = 0.0;
+        *s = 0.0; *c = 1.0;
+        bool rotated = false;
+        int cur = id;
+        while (d->hittables[cur].kind == RT_HIT_TRANSLATE || d->hittables[cur].kind == RT_HIT_ROTATE_Y) {
+            const rt_hittable_desc& x = d->hittables[cur];
+            if (x.kind == RT_HIT_TRANSLATE) {
+                if (!rotated && b[0] == 0 && b[1] == 0 && b[2] == 0) for (int k = 0; k < 3; ++k) a[k] += x.v0[k];
+                else for (int k = 0; k < 3; ++k) b[k] -= x.v0[k];
+            } else {
+                const double s2 = x.s0, c2 = x.s1;
+                const double bx = c2 * b[0] - s2 * b[2], bz = s2 * b[0] + c2 * b[2];
+                b[0] = bx; b[2] = bz;
+                if (!rotated) { *s = s2; *c = c2; }
+                else { const double ns = *s * c2 + *c * s2, nc = *c * c2 - *s * s2; *s = ns; *c = nc; }
+                rotated = true;
+            }
+            cur = x.child;
+        }
+        return cur;
+    }
+
     void emit_node(int n, bool in_boundary) {
         const rt_bvh_node_desc& node = d->bvh_nodes[n];
         if (node.object >= 0) { emit(node.object, in_boundary); return; }
@@ -194,6 +245,7 @@ struct Compiler {
             case RT_HIT_QUAD: emit_quad(id); break;
             case RT_HIT_LIST: {
                 if (h.count == 0) break;
+                if (is_cube(id)) { emit_box(id); break; }
                 const int w1 = push_box_header(tight(id), make_hdr(OP_INNER));
                 for (int i = 0; i < h.count; ++i) emit(d->list_items[h.child + i], in_boundary);
                 patch_skip(w1);
@@ -205,26 +257,8 @@ struct Compiler {
                     fail(RT_ERR_UNSUPPORTED, "an instance (Translate/RotateY) nested inside another instance's subtree is not supported by the device layout");
                     return;
                 }
-                // Fold the chain of directly nested Translate / RotateY wrappers (outermost first) into
-                // local = R(x - a) + b.
-                double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, s = 0.0, c = 1.0;
-                bool rotated = false;
-                int cur = id;
-                while (d->hittables[cur].kind == RT_HIT_TRANSLATE || d->hittables[cur].kind == RT_HIT_ROTATE_Y) {
-                    const rt_hittable_desc& x = d->hittables[cur];
-                    if (x.kind == RT_HIT_TRANSLATE) {
-                        if (!rotated && b[0] == 0 && b[1] == 0 && b[2] == 0) for (int k = 0; k < 3; ++k) a[k] += x.v0[k];
-                        else for (int k = 0; k < 3; ++k) b[k] -= x.v0[k];
-                    } else {
-                        const double s2 = x.s0, c2 = x.s1;
-                        const double bx = c2 * b[0] - s2 * b[2], bz = s2 * b[0] + c2 * b[2];
-                        b[0] = bx; b[2] = bz;
-                        if (!rotated) { s = s2; c = c2; }
-                        else { const double ns = s * c2 + c * s2, nc = c * c2 - s * s2; s = ns; c = nc; }
-                        rotated = true;
-                    }
-                    cur = x.child;
-                }
+                double a[3], b[3], s, c;
+                const int cur = fold_xform(id, a, b, &s, &c);
                 const int w1 = push_box_header(tight(id), make_hdr(OP_XFORM_ENTER));
                 push((float)a[0], (float)a[1], (float)a[2], (float)s);
                 push((float)b[0], (float)b[1], (float)b[2], (float)c);
@@ -239,25 +273,50 @@ struct Compiler {
             case RT_HIT_CONSTANT_MEDIUM: {
                 if (in_boundary) { fail(RT_ERR_UNSUPPORTED, "a ConstantMedium used as the boundary of another medium is not supported"); return; }
                 const rt_hittable_desc& bd = d->hittables[h.child];
-                const int w1 = push_box_header(tight(id), make_hdr(OP_MEDIUM));
+                double xa[3], xb[3], xs, xc;
+                const int inner = fold_xform(h.child, xa, xb, &xs, &xc);
+                const bool analytic = bd.kind == RT_HIT_SPHERE || (!in_xform && is_cube(inner));
+                // A world-space medium with an analytic boundary is evaluated once at the start of every segment
+                // instead of at its BVH position: its free-flight draw is keyed by (segment, medium), not by visit
+                // order, and closest-hit is order independent, so the result is the same and every lane of a warp
+                // runs it at the same time.
+                const bool hoist = opt.hoist_media && analytic && !in_xform && (int)hoisted_at.size() < kMaxHoistedMedia;
+                std::vector<F4> saved;
+                int w1 = -1;
+                if (hoist) { saved.swap(out->ops); hoisted_at.push_back((int32_t)hoisted.size()); }
+                else w1 = push_box_header(tight(id), make_hdr(OP_INNER));   // the medium's box, then its body
                 if (bd.kind == RT_HIT_SPHERE) {
-                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), int_to_float_bits(MEDIUM_BOUNDARY_SPHERE));
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_SPHERE)));
+                    // A medium's entry/exit distances feed a random free-flight comparison, never a surface position, so
+                    // f32 roots (relative error 1e-7) are enough even for the r = 5000 fog of final_scene.
                     uint32_t pidx = 0;
-                    const bool precise = wants_precise(bd);
-                    if (precise) pidx = (uint32_t)add_precise(bd);
+                    const bool precise = false;
                     push((float)bd.v0[0], (float)bd.v0[1], (float)bd.v0[2], (float)bd.s0);
                     const uint32_t aux = ((bd.flags & RT_FLAG_MOVING) ? FLAG_MOVING : 0u) | (precise ? FLAG_PRECISE : 0u);
                     push((float)bd.v1[0], (float)bd.v1[1], (float)bd.v1[2], int_to_float_bits((int32_t)(pidx | (aux << 24))));
+                } else if (!in_xform && is_cube(inner)) {
+                    const rt_hittable_desc& cube = d->hittables[inner];
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_XBOX)));
+                    push((float)xa[0], (float)xa[1], (float)xa[2], (float)xs);
+                    push((float)xb[0], (float)xb[1], (float)xb[2], (float)xc);
+                    push((float)cube.v0[0], (float)cube.v0[1], (float)cube.v0[2], 0.0f);
+                    push((float)cube.v1[0], (float)cube.v1[1], (float)cube.v1[2], 0.0f);
                 } else {
-                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), int_to_float_bits(MEDIUM_BOUNDARY_PROGRAM));
-                    const int w3 = here();
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_PROGRAM)));
+                    const int wb = here();
+                    push(0.0f, 0.0f, 0.0f, 0.0f);
                     push(0.0f, 0.0f, 0.0f, 0.0f);
                     const int bbegin = here();
                     emit(h.child, true);
-                    out->ops[w3].x = int_to_float_bits(bbegin);
-                    out->ops[w3].y = int_to_float_bits(here());
+                    out->ops[wb].x = int_to_float_bits(bbegin);
+                    out->ops[wb].y = int_to_float_bits(here());
                 }
-                patch_skip(w1);
+                if (hoist) {
+                    hoisted.insert(hoisted.end(), out->ops.begin(), out->ops.end());
+                    out->ops.swap(saved);
+                } else {
+                    patch_skip(w1);
+                }
                 break;
             }
             case RT_HIT_BVH: {
@@ -282,13 +341,14 @@ struct Compiler {
 
 }  // namespace
 
-int compile_scene(const rt_scene_desc* desc, CompiledScene* out, const char** err) {
+int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, CompiledScene* out, const char** err) {
     static thread_local std::string msg;
     if (!desc || !out) { msg = "compile_scene: null argument"; if (err) *err = msg.c_str(); return RT_ERR_INVALID_ARGUMENT; }
     if (desc->abi_version != RT_B200_ABI_VERSION) { msg = "rt_scene_desc.abi_version mismatch"; if (err) *err = msg.c_str(); return RT_ERR_INVALID_ARGUMENT; }
     Compiler c;
     c.d = desc;
     c.out = out;
+    c.opt = opt;
     c.tight_hittable.resize(desc->n_hittables);
     c.have_h.assign(desc->n_hittables, 0);
     c.tight_node.resize(desc->n_bvh_nodes);
@@ -345,6 +405,49 @@ int compile_scene(const rt_scene_desc* desc, CompiledScene* out, const char** er
         out->ops.push_back(F4{-inf, -inf, -inf, int_to_float_bits(2)});
     }
     if (c.status) { msg = c.err; if (err) *err = msg.c_str(); return c.status; }
+
+    // successor classes into the header bits (dev_scene.h)
+    {
+        std::vector<F4>& ops = out->ops;
+        if (ops.empty()) {   // nothing but hoisted media (or nothing at all): keep one unhittable node
+            const float inf = std::numeric_limits<float>::infinity();
+            ops.push_back(F4{inf, inf, inf, bits_to_float(make_hdr(OP_INNER))});
+            ops.push_back(F4{-inf, -inf, -inf, int_to_float_bits(2)});
+        }
+        const int n = (int)ops.size();
+        auto hdr_of = [&](int i) { uint32_t u; std::memcpy(&u, &ops[i].w, 4); return u; };
+        auto int_of = [&](float f) { int32_t v; std::memcpy(&v, &f, 4); return v; };
+        auto cls_at = [&](int i) -> uint32_t { return i >= n ? (uint32_t)CLS_SHADE : class_of_kind(hdr_of(i) & 15u); };
+        int i = 0;
+        while (i < n) {
+            const uint32_t hdr = hdr_of(i);
+            const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
+            int size = 2, skip = -1;
+            switch (kind) {
+                case OP_INNER: size = 2; skip = int_of(ops[i + 1].w); break;
+                case OP_SPHERE: size = (flags & FLAG_MOVING) ? 3 : 2; break;
+                case OP_QUAD: size = 4; break;
+                case OP_XFORM_ENTER: size = 4; skip = int_of(ops[i + 1].w); break;
+                case OP_XFORM_EXIT: size = 2; break;
+                case OP_MEDIUM: size = (int)flags == MEDIUM_BOUNDARY_XBOX ? 5 : 3; break;
+                case OP_BOX: size = 3; break;
+                default: msg = "internal: bad op kind in stream"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL;
+            }
+            int ft = i + size;
+            if (kind == OP_MEDIUM && (int)flags == MEDIUM_BOUNDARY_PROGRAM) ft = int_of(ops[i + 1].y);   // run past the inline program
+            const uint32_t ft_cls = cls_at(ft), sk_cls = skip >= 0 ? cls_at(skip) : ft_cls;
+            const uint32_t nh = (hdr & 0xffu) | (ft_cls << 8) | (sk_cls << 11);
+            std::memcpy(&ops[i].w, &nh, 4);
+            i += size;
+        }
+        if (i != n) { msg = "internal: op stream walk ended off the end"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL; }
+        out->first_class = cls_at(0);
+        out->n_world_words = n;
+        for (int32_t off : c.hoisted_at) out->hoisted_media.push_back(n + off);
+        ops.insert(ops.end(), c.hoisted.begin(), c.hoisted.end());
+        ops.push_back(F4{0.0f, 0.0f, 0.0f, 0.0f});   // padding: the render kernel fetches two words at the cursor
+        ops.push_back(F4{0.0f, 0.0f, 0.0f, 0.0f});   // unconditionally, including at the end of the world program
+    }
 
     for (int i = 0; i < desc->n_materials; ++i) {
         const rt_material_desc& m = desc->materials[i];
