@@ -39,6 +39,19 @@ def flops_per_path():
         return None, "missing"
 
 
+# SURVEY.md §8(d) cost table applied to the ops the DEVICE traversal executes (rt_render_count_ops), so that
+# roofline.achieved counts arithmetic the kernel really does. The reference visits far more nodes for the same
+# image (per-axis AABB quirk, origin-inclusive list boxes, 6 quads per box), see profiles/flops_per_path.json.
+DEVICE_COST = {"slab": 24, "box": 24, "box_hit": 8, "sphere": 24, "sphere_moving": 6, "sphere_hit": 8, "quad": 16, "quad_hit": 50,
+               "xform_enter": 15, "finalize_xform": 12, "medium": 56, "medium_hit": 8, "lambertian": 42 + 30, "metal": 57 + 30,
+               "dielectric": 60 + 30, "isotropic": 33 + 30, "light": 30, "tex_noise": 850, "tex_image": 12, "tex_checker": 9,
+               "segments": 9 + 3, "paths": 31}
+
+
+def device_flops_per_path(counts):
+    return sum(DEVICE_COST.get(k, 0) * v for k, v in counts.items()) / max(1, counts["paths"])
+
+
 def ncu_traffic_per_launch():
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
@@ -284,12 +297,19 @@ def main():
             peak, peak_src = NOMINAL_FP32_TFLOPS, "nominal 148 SMs x 128 x 2 x 1.965 GHz"
         kern_s = float(t_kernel.item()) * 1e-3 / args.steps
         paths_per_launch = h * w * count
-        roofline = {"bound": "fp32", "kernel": "render_kernel", "unit": "TFLOP/s", "peak": peak, "peak_source": peak_src,
-                    "peak_nominal": NOMINAL_FP32_TFLOPS, "achieved": None, "frac": None, "traffic": None,
-                    "flops_per_path": fpp, "flops_per_path_source": fpp_src, "kernel_ms_per_launch": kern_s * 1e3}
-        if fpp:
-            roofline["achieved"] = fpp * paths_per_launch / kern_s / 1e12
-            roofline["frac"] = roofline["achieved"] / peak
+        ops = ctx.count_ops(ds, cam, 0, 4, seed=0)          # instrumented kernel, outside every timed region
+        dfpp = device_flops_per_path(ops)
+        roofline = {"bound": "fp32", "kernel": "render_kernel_v3", "unit": "TFLOP/s", "peak": peak, "peak_source": peak_src,
+                    "peak_nominal": NOMINAL_FP32_TFLOPS,
+                    "achieved": dfpp * paths_per_launch / kern_s / 1e12, "frac": dfpp * paths_per_launch / kern_s / 1e12 / peak,
+                    "traffic": None, "flops_per_path": dfpp,
+                    "flops_per_path_source": "device op counts (rt_render_count_ops, 4 spp) x SURVEY.md 8(d) cost table",
+                    "device_ops_per_path": {k: v / ops["paths"] for k, v in ops.items()},
+                    "kernel_ms_per_launch": kern_s * 1e3}
+        if fpp:   # the same image at the reference's own visit counts (oracle-counted): a work-rate, not a utilisation
+            roofline["reference_flops_per_path"] = fpp
+            roofline["reference_flops_per_path_source"] = fpp_src
+            roofline["reference_equivalent_tflops"] = fpp * paths_per_launch / kern_s / 1e12
         tr = ncu_traffic_per_launch()
         if tr:
             roofline["traffic"] = tr.get("dram_bytes_per_launch")

@@ -24,7 +24,13 @@ def main():
     s, cs = rt.builtin_scene(a.scene, image_width=a.width, max_depth=a.depth, earth=earth)
     cam = rt.Camera(cs)
     ctx = rt.Context(0)
+    t0 = time.time()
     ds = ctx.upload(s)
+    print(f"upload {1e3 * (time.time() - t0):.1f} ms", flush=True)
+    t0 = time.time()
+    ds.close()
+    ds = ctx.upload(s)
+    print(f"close+upload again {1e3 * (time.time() - t0):.1f} ms", flush=True)
     for r in range(a.reps):
         t0 = time.time()
         img = ctx.render(ds, cam, 0, a.spp, seed=r)
