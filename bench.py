@@ -311,9 +311,10 @@ def main():
             roofline["reference_flops_per_path_source"] = fpp_src
             roofline["reference_equivalent_tflops"] = fpp * paths_per_launch / kern_s / 1e12
         tr = ncu_traffic_per_launch()
-        if tr:
-            roofline["traffic"] = tr.get("dram_bytes_per_launch")
-            roofline["traffic_note"] = tr.get("note")
+        if tr:   # DRAM bytes per path from the committed ncu --set full capture, scaled to this launch's path count
+            roofline["traffic"] = tr.get("dram_bytes_per_path", 0.0) * paths_per_launch
+            roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per path from profiles/ncu_traffic.json ("
+                                        + str(tr.get("capture")) + ") x paths of this launch; HBM is not the bound of this kernel")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import binding as ob
