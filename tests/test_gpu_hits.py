@@ -204,3 +204,16 @@ def test_bvh_export_matches_description(rt, ctx, earth):
         got = ctx.bvh_export(ds, b)
         assert np.array_equal(got, np.array(want, dtype=np.int32))
     ds.close()
+
+
+@pytest.mark.parametrize("idx", [0, 7, 8])
+def test_hit_parity_one_million_rays(rt, ob, ctx, earth, idx):
+    """The batch size SURVEY.md §8(d) names: 2^20 rays per scene (seed 7), half camera rays, half secondary-like."""
+    s, cam = small_scene(rt, idx, earth)
+    ds = ctx.upload(s)
+    rays = make_rays(cam, s.desc, 1 << 20, seed=7)
+    ref = ob.hit_batch(s.desc, rays, seed=7)
+    dev = ctx.hit_batch(ds, rays, seed=7)
+    stats = check_hits(dev, ref, rays, max_inequivalent=64)
+    assert stats["flips"] <= 8
+    ds.close()
