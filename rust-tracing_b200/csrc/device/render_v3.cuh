@@ -1,6 +1,12 @@
-// K1 v3: the class-voting state machine of render_v2.cuh rebuilt for occupancy.
+// K1: the render loop (renderer.rs:26-49,139-155) as a per-lane state machine with warp-level class voting.
 //
-// What changed against v2 (ncu: 120 registers -> 4 warps per scheduler, 'wait' + 'branch_resolving' stalls
+// Every lane is always somewhere in {a traversal op of some class, waiting to shade / get a new path}. Each
+// iteration the warp counts its lanes per class, runs only the most populated class (lanes of other classes wait,
+// which costs no issue slots), and lanes whose op finished move on to their next op's class - known from the header
+// bits before the op's words arrive (dev_scene.h). Lanes regroup by what they are about to execute instead of
+// idling behind the longest traversal or the rarest op kind of the warp. This is the third form of the kernel:
+//
+// what changed against the second (ncu: 120 registers -> 4 warps per scheduler, 'wait' + 'branch_resolving' stalls
 // dominate, issue slots 52% busy):
 //  * cold per-path state (world-space ray, radiance sum, throughput, RNG key, pixel, depth, time) lives in
 //    shared memory, one SoA column per thread, and is touched only when a segment is shaded; the traversal
@@ -10,8 +16,9 @@
 //  * the vote takes a one-ballot fast path while the slab class holds enough lanes;
 //  * the op stream carries two padding words so the next op's words are fetched unconditionally.
 //
-// Included by rt_cuda.cu after render_v2.cuh.
+// Included by rt_cuda.cu.
 #pragma once
+
 
 constexpr int kColdFields = 20;   // so(3) sd(3) L(3) Tp(3) key(4) time pix depth origin_unused
 

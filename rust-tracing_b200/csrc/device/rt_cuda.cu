@@ -1,10 +1,10 @@
 // Kernels + device half of the C ABI (include/rt_b200.h).
 //
-// K1 render_kernel   persistent megakernel: the parallel loop of renderer.rs:26-49. One warp owns a
-//                    pool of (8x4 pixel tile) x (sample chunk) paths at a time; a lane whose path ends
-//                    takes the next path of the pool in the same iteration (ballot/popc ranking), so
-//                    lanes never idle on finished paths. Radiance sums go to a float4 framebuffer with
-//                    one vector reduction per path.
+// K1 render_kernel_v3 (render_v3.cuh): persistent megakernel for the parallel loop of renderer.rs:26-49. One
+//                    warp owns a pool of (8x4 pixel tile) x (sample chunk) paths; a lane whose path ends takes
+//                    the next path of the pool in the same iteration (ballot/popc ranking); lanes regroup by op
+//                    class through a warp vote. Radiance sums go to a float4 framebuffer, one vector reduction
+//                    per path. render_kernel below is the first, whole-segment-per-iteration form (A/B only).
 // K2 hit_kernel      Hittable::hit on a ray batch (parity).
 // K3 finalize_kernel color_to_rgb(sum/spp) (color.rs:12-19, renderer.rs:55-58).
 // K4 texture_kernel / get_ray_kernel (parity), expand_image_kernel (upload), fma_peak_kernel.
@@ -174,7 +174,6 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
     }
 }
 
-#include "render_v2.cuh"
 #include "render_v3.cuh"
 
 struct DevRayIn { float ox, oy, oz, dx, dy, dz, time, pad; };
@@ -294,16 +293,6 @@ DevCamera make_dev_camera(const rt_camera_desc& c) {
 }  // namespace
 
 typedef void (*render_fn)(const RenderParams);
-static render_fn v2_kernel(bool counting, int min_blocks) {
-    if (counting) return render_kernel_v2<true, 1>;
-    switch (min_blocks) {
-        case 8: return render_kernel_v2<false, 8>;
-        case 6: return render_kernel_v2<false, 6>;
-        case 5: return render_kernel_v2<false, 5>;
-        default: return render_kernel_v2<false, 4>;
-    }
-}
-
 static render_fn v3_kernel(bool counting, int min_blocks) {
     if (counting) return render_kernel_v3<true, 1>;
     switch (min_blocks) {
@@ -320,7 +309,7 @@ struct rt_context {
     int clock_khz = 0;
     size_t total_mem = 0;
     int blocks_per_sm = 1;       // of the selected production kernel
-    int variant = 3;             // 3: render_v3.cuh (product); 2: render_v2.cuh; 1: one-segment-per-iteration loop (A/B only)
+    int variant = 3;             // 3: render_v3.cuh (product); 1: whole-segment-per-iteration loop (kept for A/B runs)
     int min_blocks = 5;          // occupancy variant: resident 128-thread blocks per SM the kernel is compiled for
     bool hoist_media = true;
     int shade_min = 24;
@@ -360,7 +349,7 @@ int rt_context_create(int device_id, rt_context** out) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
     c->clock_khz = khz;
     // development switches (A/B runs; the defaults are the product)
-    if (const char* e = std::getenv("RT_B200_KERNEL")) { const int v = std::atoi(e); c->variant = v == 1 ? 1 : v == 2 ? 2 : 3; }
+    if (const char* e = std::getenv("RT_B200_KERNEL")) c->variant = std::atoi(e) == 1 ? 1 : 3;
     if (const char* e = std::getenv("RT_B200_SHADE_MIN")) c->shade_min = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_SLAB_FAST")) c->slab_fast = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_SLAB_REPS")) c->slab_reps = std::max(1, std::atoi(e));
@@ -369,17 +358,11 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
     if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 6 ? 6 : v >= 5 ? 5 : 4; }
     CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    CU(cudaFuncSetAttribute(v2_kernel(false, 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    CU(cudaFuncSetAttribute(v2_kernel(false, 5), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    CU(cudaFuncSetAttribute(v2_kernel(false, 6), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    CU(cudaFuncSetAttribute(v2_kernel(false, 8), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    CU(cudaFuncSetAttribute(v2_kernel(true, 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
     for (int mb : {4, 5, 6, 8})
         CU(cudaFuncSetAttribute(v3_kernel(false, mb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     CU(cudaFuncSetAttribute(v3_kernel(true, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     int bps = 0;
     if (c->variant == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_kernel, kBlockThreads, perlin_smem_bytes()));
-    else if (c->variant == 2) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v2_kernel(false, c->min_blocks), kBlockThreads, perlin_smem_bytes()));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v3_kernel(false, c->min_blocks), kBlockThreads, v3_smem_bytes(1)));
     c->blocks_per_sm = bps > 0 ? bps : 1;
     CU(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
@@ -525,10 +508,8 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, kBlockThreads, smem));
         grid = c->sm_count * (bps > 0 ? bps : 1);
         fn<<<grid, kBlockThreads, smem, stream>>>(prm);
-    } else if (c->variant == 1) {
-        render_kernel<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
     } else {
-        v2_kernel(false, c->min_blocks)<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
+        render_kernel<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
     }
     CU(cudaGetLastError());
     c->launches += 1;
