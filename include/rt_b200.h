@@ -272,6 +272,18 @@ int rt_device_info(rt_context* ctx, int* sm_count, int* sm_clock_khz, size_t* to
 int rt_scene_upload(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out);
 void rt_scene_destroy(rt_scene* scene);
 
+/* What rt_scene_upload would build for this description, computed on the host (no GPU needed): sizes of the device
+ * layout and how many ops of each kind the flattened traversal stream holds. Fails with the same status as
+ * rt_scene_upload for descriptions the device layout cannot express (RT_ERR_UNSUPPORTED) or that are malformed. */
+typedef struct rt_layout_info {
+    int32_t n_words;            /* float4 words of the op stream (world program) */
+    int32_t n_inner, n_sphere, n_quad, n_box, n_xform, n_medium_in_stream, n_medium_hoisted;
+    int32_t n_precise_spheres;  /* spheres tested in f64 (radius > 200) */
+    int32_t n_bvh;              /* BVH hittables reachable from the world */
+    int64_t device_bytes;       /* op stream + materials + textures + Perlin tables + image texels (float4) */
+} rt_layout_info;
+int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out);
+
 /* Render samples [sample_begin, sample_begin+sample_count) of every pixel and ADD the
  * per-pixel sums into a device float4 buffer (x,y,z = radiance sum, w = sample count),
  * W*H elements row-major (pos = j*W + i, renderer.rs:32-33). Asynchronous on `stream`

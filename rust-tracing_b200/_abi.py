@@ -103,6 +103,13 @@ class SceneRequest(C.Structure):
                 ("earth_rgb8", C.POINTER(C.c_uint8))]
 
 
+class LayoutInfo(C.Structure):
+    _fields_ = [("n_words", C.c_int32), ("n_inner", C.c_int32), ("n_sphere", C.c_int32), ("n_quad", C.c_int32),
+                ("n_box", C.c_int32), ("n_xform", C.c_int32), ("n_medium_in_stream", C.c_int32),
+                ("n_medium_hoisted", C.c_int32), ("n_precise_spheres", C.c_int32), ("n_bvh", C.c_int32),
+                ("device_bytes", C.c_int64)]
+
+
 class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("last_kernel_ms", C.c_float)]
@@ -156,6 +163,7 @@ PROTOTYPES = {
     "rt_device_info": (C.c_int, [vp, P(C.c_int), P(C.c_int), P(C.c_size_t)]),
     "rt_scene_upload": (C.c_int, [vp, P(SceneDesc), P(vp)]),
     "rt_scene_destroy": (None, [vp]),
+    "rt_scene_layout": (C.c_int, [P(SceneDesc), P(LayoutInfo)]),
     "rt_render_accumulate": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp, vp]),
     "rt_render": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp]),
     "rt_finalize_rgb8": (C.c_int, [vp, vp, C.c_int64, C.c_double, vp]),

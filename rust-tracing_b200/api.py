@@ -246,6 +246,13 @@ def builtin_scene(scene, image_width=0, samples_per_pixel=0, max_depth=0, scene_
     return s, settings
 
 
+def scene_layout(scene):
+    """Host-side dry run of the flattening rt_scene_upload performs (no GPU): dict of op counts and sizes."""
+    info = A.LayoutInfo()
+    A.check(A.lib().rt_scene_layout(C.byref(scene.desc), C.byref(info)))
+    return {name: getattr(info, name) for name, _ in A.LayoutInfo._fields_}
+
+
 class DeviceScene:
     def __init__(self, ctx, scene):
         self.ctx = ctx

@@ -465,6 +465,40 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     return RT_OK;
 }
 
+int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out) {
+    if (!desc || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_layout: null argument");
+    CompiledScene cs;
+    const char* err = nullptr;
+    const int rc = compile_scene(desc, CompileOptions(), &cs, &err);
+    if (rc < 0) return fail(rc, err ? err : "compile_scene failed");
+    std::memset(out, 0, sizeof(*out));
+    out->n_words = cs.n_world_words;
+    const int n_all = (int)cs.ops.size() - 2;   // without the two padding words
+    for (int i = 0; i < cs.n_world_words;) {
+        uint32_t hdr;
+        std::memcpy(&hdr, &cs.ops[i].w, 4);
+        const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
+        switch (kind) {
+            case OP_INNER: out->n_inner++; i += 2; break;
+            case OP_SPHERE: out->n_sphere++; i += (flags & FLAG_MOVING) ? 3 : 2; break;
+            case OP_QUAD: out->n_quad++; i += 4; break;
+            case OP_XFORM_ENTER: out->n_xform++; i += 4; break;
+            case OP_XFORM_EXIT: i += 2; break;
+            case OP_MEDIUM: out->n_medium_in_stream++; i += (int)flags == MEDIUM_BOUNDARY_XBOX ? 5 : 3; break;
+            case OP_BOX: out->n_box++; i += 3; break;
+            default: return fail(RT_ERR_INTERNAL, "rt_scene_layout: bad op in stream");
+        }
+    }
+    out->n_medium_hoisted = (int32_t)cs.hoisted_media.size();
+    out->n_precise_spheres = (int32_t)cs.precise.size() / 2;
+    out->n_bvh = (int32_t)cs.bvh_hittable_ids.size();
+    int64_t bytes = (int64_t)(n_all + 2) * 16 + (int64_t)(cs.materials.size() + cs.textures.size() + cs.perlin_vec.size()) * 16 +
+                    (int64_t)cs.perlin_perm.size() + (int64_t)cs.precise.size() * 32;
+    for (int k = 0; k < desc->n_images; ++k) bytes += (int64_t)desc->images[k].width * desc->images[k].height * 16;
+    out->device_bytes = bytes;
+    return RT_OK;
+}
+
 void rt_scene_destroy(rt_scene* s) {
     if (!s) return;
     if (s->ctx) cudaSetDevice(s->ctx->device);

@@ -435,6 +435,13 @@ int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, Compiled
             }
             int ft = i + size;
             if (kind == OP_MEDIUM && (int)flags == MEDIUM_BOUNDARY_PROGRAM) ft = int_of(ops[i + 1].y);   // run past the inline program
+            // the kernels follow these links without bounds checks: every successor must lie in (i, n]
+            if (i + size > n || ft <= i || ft > n || (skip >= 0 && (skip <= i || skip > n))) {
+                msg = "internal: op stream link out of range"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL;
+            }
+            if (kind == OP_MEDIUM && (int)flags == MEDIUM_BOUNDARY_PROGRAM && (int_of(ops[i + 1].x) != i + 3 || ft < i + 3)) {
+                msg = "internal: medium boundary program out of range"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL;
+            }
             const uint32_t ft_cls = cls_at(ft), sk_cls = skip >= 0 ? cls_at(skip) : ft_cls;
             const uint32_t nh = (hdr & 0xffu) | (ft_cls << 8) | (sk_cls << 11);
             std::memcpy(&ops[i].w, &nh, 4);

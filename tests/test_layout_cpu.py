@@ -1,0 +1,71 @@
+"""The flattening that rt_scene_upload performs (scene description -> threaded op stream), dry-run on the host:
+op counts per scene, the cube -> slab-primitive rewrite, media hoisting, f64 flags, and rejected nestings."""
+import numpy as np
+import pytest
+
+from conftest import small_scene
+
+
+def test_final_scene_layout(rt):
+    s, _ = small_scene(rt, 8, rt.synthetic_earth(64, 32))
+    L = rt.scene_layout(s)
+    assert L["n_box"] == 400                      # 400 Quad::cube lists -> 400 slab primitives (2400 quads in the description)
+    assert L["n_quad"] == 1                       # the light
+    assert L["n_sphere"] == 1000 + 6              # box of spheres + moving, glass, metal, r=70 boundary, earth, noise
+    assert L["n_inner"] == 399 + 999 + 10         # branch nodes of the three BVHs (leaves carry no box of their own)
+    assert L["n_xform"] == 1 and L["n_bvh"] == 3
+    assert L["n_medium_hoisted"] == 2 and L["n_medium_in_stream"] == 0
+    assert L["n_precise_spheres"] == 0            # the r=5000 fog boundary only feeds a free-flight comparison: f32
+    assert L["device_bytes"] < 400_000            # everything but full-size texels fits L1/L2 (earth here is a 64x32 stand-in)
+
+
+def test_other_scenes_layout(rt):
+    L0 = rt.scene_layout(small_scene(rt, 0)[0])
+    assert L0["n_precise_spheres"] == 1 and L0["n_box"] == 0 and L0["n_sphere"] == L0["n_inner"] + 1
+    L6 = rt.scene_layout(small_scene(rt, 6)[0])
+    assert (L6["n_quad"], L6["n_box"], L6["n_xform"], L6["n_inner"]) == (6, 2, 2, 7)
+    L7 = rt.scene_layout(small_scene(rt, 7)[0])
+    assert (L7["n_quad"], L7["n_box"], L7["n_xform"], L7["n_medium_hoisted"]) == (6, 0, 0, 2)   # boxes only bound media
+
+
+def test_degenerate_cube_keeps_its_quads(rt):
+    s = rt.Scene()
+    m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))
+    s.finish(s.cube((0, 0, 0), (1, 0, 1), m))     # flat in y: not a slab primitive
+    L = rt.scene_layout(s)
+    assert L["n_box"] == 0 and L["n_quad"] == 6
+
+
+def test_media_inside_instances_stay_in_the_stream(rt):
+    s = rt.Scene()
+    m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))
+    med = s.ConstantMedium(s.Sphere((0, 0, 0), 1.0, m), 0.5, (1, 1, 1))
+    s.finish(s.Translate(med, (3, 0, 0)))
+    L = rt.scene_layout(s)
+    assert L["n_medium_in_stream"] == 1 and L["n_medium_hoisted"] == 0 and L["n_xform"] == 1
+
+
+def test_unsupported_nesting_rejected_on_the_host(rt):
+    s = rt.Scene()
+    m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))
+    inner = rt.HittableList()
+    inner.add(s.Translate(s.Sphere((0, 0, 0), 1.0, m), (1, 0, 0)))
+    inner.add(s.Sphere((3, 0, 0), 1.0, m))
+    s.finish(s.RotateY(s.BVHNode(inner), 10.0))
+    with pytest.raises(rt._abi.RtError) as e:
+        rt.scene_layout(s)
+    assert e.value.status == rt._abi.RT_ERR_UNSUPPORTED
+    s2 = rt.Scene()
+    m2 = s2.Lambertian(s2.SolidColor(0.5, 0.5, 0.5))
+    inner_med = s2.ConstantMedium(s2.Sphere((0, 0, 0), 1.0, m2), 0.5, (1, 1, 1))
+    s2.finish(s2.ConstantMedium(inner_med, 0.5, (1, 1, 1)))       # a medium bounding a medium
+    with pytest.raises(rt._abi.RtError) as e2:
+        rt.scene_layout(s2)
+    assert e2.value.status == rt._abi.RT_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_every_cli_scene_flattens(rt, idx):
+    s, _ = small_scene(rt, idx, rt.synthetic_earth(64, 32))
+    L = rt.scene_layout(s)
+    assert L["n_words"] >= 2 and L["n_bvh"] >= 1
