@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "csrc", "librt_b200.so")   # RT_B200_LIB: development variants only
 
 RT_OK = 0
 RT_ERR_INVALID_ARGUMENT = -1

@@ -27,7 +27,10 @@ DEPS = SOURCES + [
     os.path.join(HERE, "..", "include", "rt_b200.hpp"),
 ]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+# -prec-div=false -prec-sqrt=false: device divisions / square roots use the 1-2 ulp fast sequences instead of the
+# IEEE-rounded ones (+8-10% Mpaths/s on every scene, profiles/r1_ab12*.log); the GPU parity suite passes unchanged
+# within its stated tolerances. Denormals and FMA contraction keep their defaults.
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-prec-div=false", "-prec-sqrt=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-Xptxas", "-v"]
 
 
@@ -38,10 +41,12 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: development variants (e.g. -DRT_OPT_... into csrc/librt_b200_<name>.so, selected at run time
+    with RT_B200_LIB=<path>); the product is always the default build."""
+    if out is None and not force and up_to_date():
         return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT] + SOURCES
+    cmd = [NVCC] + FLAGS + list(extra_flags) + ["-o", out or OUT] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(CSRC, "build.log")
     with open(log, "w") as f:
@@ -50,9 +55,15 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed (see {log})")
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
-    print(OUT)
+    if "--variant" in sys.argv:      # python build.py --variant NAME -DFLAG ...   -> csrc/librt_b200_NAME.so
+        k = sys.argv.index("--variant")
+        name = sys.argv[k + 1]
+        print(build(force=True, verbose="-v" in sys.argv, extra_flags=[a for a in sys.argv[k + 2:] if a != "-v"],
+                    out=os.path.join(CSRC, f"librt_b200_{name}.so")))
+    else:
+        build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
+        print(OUT)

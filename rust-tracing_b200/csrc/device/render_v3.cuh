@@ -20,6 +20,7 @@
 #pragma once
 
 
+constexpr int kSlabReps = 8;       // consecutive slab-class ops per vote (8 and 16 measured equal, 4 slower)
 constexpr int kColdFields = 20;   // so(3) sd(3) L(3) Tp(3) key(4) time pix depth origin_unused
 
 inline size_t v3_smem_bytes(int n_perlin) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
 
         if (pick == CLS_SLAB) {
 #pragma unroll 1
-            for (int rep = 0; rep < prm.slab_reps; ++rep) {
+                        for (int rep = 0; rep < kSlabReps; ++rep) {
                 if (cls == CLS_SLAB) {
                     const uint32_t hdr = (uint32_t)fbits(w0.w);
                     const uint32_t kind = hdr & 15u;

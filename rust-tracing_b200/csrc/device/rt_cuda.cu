@@ -25,7 +25,11 @@ using rt_host::fail;
 
 namespace {
 
+#ifdef RT_OPT_BLOCK
+constexpr int kBlockThreads = RT_OPT_BLOCK;
+#else
 constexpr int kBlockThreads = 128;
+#endif
 constexpr int kTileW = 8, kTileH = 4;
 constexpr int kMaxPerlinShared = 4;
 
@@ -44,7 +48,7 @@ struct RenderParams {
     int first_class;             // OpClass of op 0
     int shade_min;               // the shade class may win the vote once this many lanes wait for it
     int slab_fast;               // v3: lanes in the slab class that skip the full vote
-    int slab_reps, sphere_reps;  // v3: consecutive ops a class may run per vote
+    int slab_reps, sphere_reps;  // v3: consecutive ops a class may run per vote (slab: compile-time kSlabReps)
 };
 
 // op counters of the instrumented kernel (rt_render_count_ops): what the device traversal actually executes
@@ -516,11 +520,13 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     prm.sample_count = (int)sample_count;
     prm.tiles_x = (prm.cam.width + kTileW - 1) / kTileW;
     prm.tiles_y = (prm.cam.height + kTileH - 1) / kTileH;
-    // pool = tile x chunk samples; keep enough items (>= 8 per resident warp) for the tail to stay short
+    // pool = tile x chunk samples; keep >= 64 pools per resident warp so the tail of the launch (warps running dry
+    // while others still hold a pool) stays near 1%: short renders get small chunks, the 10000-spp bench keeps 32
     const int64_t n_tiles = (int64_t)prm.tiles_x * prm.tiles_y;
     const int64_t resident_warps = (int64_t)c->sm_count * c->blocks_per_sm * (kBlockThreads / 32);
     int chunk = 32;
-    while (chunk > 1 && n_tiles * ((sample_count + chunk - 1) / chunk) < resident_warps * 8) chunk >>= 1;
+    if (const char* e = std::getenv("RT_B200_CHUNK")) chunk = std::max(1, std::atoi(e));
+    while (chunk > 1 && n_tiles * ((sample_count + chunk - 1) / chunk) < resident_warps * 64) chunk >>= 1;
     prm.chunk = chunk;
     prm.n_chunks = (int)((sample_count + chunk - 1) / chunk);
     if ((uint64_t)n_tiles * (uint64_t)prm.n_chunks >= 0xffffffffull) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: too many work items; split the sample range");
