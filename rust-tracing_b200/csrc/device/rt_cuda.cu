@@ -301,6 +301,7 @@ static render_fn v3_kernel(bool counting, int min_blocks) {
     if (counting) return render_kernel_v3<true, 1>;
     switch (min_blocks) {
         case 8: return render_kernel_v3<false, 8>;
+        case 7: return render_kernel_v3<false, 7>;
         case 6: return render_kernel_v3<false, 6>;
         case 5: return render_kernel_v3<false, 5>;
         default: return render_kernel_v3<false, 4>;
@@ -314,7 +315,7 @@ struct rt_context {
     size_t total_mem = 0;
     int blocks_per_sm = 1;       // of the selected production kernel
     int variant = 3;             // 3: render_v3.cuh (product); 1: whole-segment-per-iteration loop (kept for A/B runs)
-    int min_blocks = 5;          // occupancy variant: resident 128-thread blocks per SM the kernel is compiled for
+    int min_blocks = 6;          // occupancy variant: resident 128-thread blocks per SM the kernel is compiled for
     bool hoist_media = true;
     int shade_min = 24;
     int slab_fast = 14, slab_reps = 8, sphere_reps = 2;
@@ -360,9 +361,9 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* e = std::getenv("RT_B200_SPHERE_REPS")) c->sphere_reps = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_NO_BOX")) c->box_primitives = std::atoi(e) == 0;
     if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
-    if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 6 ? 6 : v >= 5 ? 5 : 4; }
+    if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 4 ? v : 4; }
     CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    for (int mb : {4, 5, 6, 8})
+    for (int mb : {4, 5, 6, 7, 8})
         CU(cudaFuncSetAttribute(v3_kernel(false, mb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     CU(cudaFuncSetAttribute(v3_kernel(true, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     int bps = 0;
