@@ -10,7 +10,8 @@ REPS = [('r1_a_v1_whole_segment_loop', 'prof_r1_a.ncu-rep', 'v1: every lane trac
         ('r1_b_v2_class_voting', 'prof_r1_b.ncu-rep', 'v2: class-voting state machine + cube slab primitive'),
         ('r1_c4_v3_128regs', 'prof_r1_c4.ncu-rep', 'v3 @ 4 blocks/SM (cold state in shared memory), before the code-size work'),
         ('r1_c6_v3_80regs', 'prof_r1_c6.ncu-rep', 'v3 @ 6 blocks/SM, before the code-size work (I-cache thrash)'),
-        ('r1_d_v3_default', 'prof_r1_d.ncu-rep', 'v3 @ 5 blocks/SM after shrinking the instruction footprint (current default)')]
+        ('r1_d_v3_small_code', 'prof_r1_d.ncu-rep', 'v3 @ 5 blocks/SM after shrinking the instruction footprint'),
+        ('r1_e_v3_default', 'prof_r1_e.ncu-rep', 'v3 @ 6 blocks/SM, fast div/sqrt build (current default)')]
 KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
@@ -78,7 +79,7 @@ def main():
         g(d, 'smsp__issue_active.avg.pct_of_peak_sustained_active'), g(d, 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio'),
         g(d, 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio'), g(d, 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio'),
         g(d, 'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio'), g(d, 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio')))
-    L.append('* I-cache: `no_instruction` was 3.26 (v3, 4 blocks) and 6.55 (6 blocks) before the instruction-footprint work, 0.90 after; that change alone took the launch from 62.1 ms to 43.4 ms.')
+    L.append('* I-cache: `no_instruction` was 3.26 (v3, 4 blocks) and 6.55 (6 blocks) before the instruction-footprint work and 0.90 right after it (r1_d); that change alone took the launch from 62.1 ms to 43.4 ms.')
     dram = (g(d, 'dram__bytes_read.sum') + g(d, 'dram__bytes_write.sum')) * 1e6
     L.append('* Memory: L1 hit {:.1f}%, L2 hit {:.1f}%, DRAM traffic {:.0f} MB per launch = {:.1f} B per path (earth texels and the framebuffer reductions); HBM is idle.'.format(
         g(d, 'l1tex__t_sector_hit_rate.pct'), g(d, 'lts__t_sector_hit_rate.pct'), dram / 1e6, dram / PATHS))
