@@ -21,7 +21,7 @@
 
 
 constexpr int kSlabReps = 8;       // consecutive slab-class ops per vote (8 and 16 measured equal, 4 slower)
-constexpr int kColdFields = 20;   // so(3) sd(3) L(3) Tp(3) key(4) time pix depth origin_unused
+constexpr int kColdFields = 16;   // world o(3) d(3), L(3), Tp(3), sample index, time, pixel, depth (the RNG key is re-derived from pixel, sample)
 
 inline size_t v3_smem_bytes(int n_perlin) {
     const int np = n_perlin < kMaxPerlinShared ? n_perlin : kMaxPerlinShared;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                     CNT(K_SPHERE);
                     if (COUNT) { if ((hdr >> 4) & FLAG_MOVING) cnt[K_SPHERE_MOVING]++; if ((hdr >> 4) & FLAG_PRECISE) cnt[K_SPHERE_PRECISE]++; }
                     const float tb = T.best.t;
-                    op_sphere(S, T, w0, w1, COLD(16), tmin, origin);
+                    op_sphere(S, T, w0, w1, COLD(13), tmin, origin);
                     if (COUNT && T.best.t != tb) cnt[K_SPHERE_HIT]++;
                     cls = (hdr >> 8) & 7u;
                     FETCH_NEXT();
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                 const uint32_t hdr = (uint32_t)fbits(w0.w);
                 CNT(K_MEDIUM);
                 const float tb = T.best.t;
-                const uint4 key = make_uint4(COLD_U(12), COLD_U(13), COLD_U(14), COLD_U(15));
-                op_medium(S, T, w0, w1, COLD(16), tmin, key, COLD_U(18));
+                const uint4 key = path_key(prm.seed, COLD_U(14), COLD_U(12));
+                op_medium(S, T, w0, w1, COLD(13), tmin, key, COLD_U(15));
                 if (COUNT && T.best.t != tb) cnt[K_MEDIUM_HIT]++;
                 cls = (hdr >> 8) & 7u;
                 FETCH_NEXT();
@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                 Ray ray;
                 ray.o = f3(COLD(0), COLD(1), COLD(2));
                 ray.d = f3(COLD(3), COLD(4), COLD(5));
-                ray.time = COLD(16);
+                ray.time = COLD(13);
                 float3 L = f3(COLD(6), COLD(7), COLD(8)), Tp = f3(COLD(9), COLD(10), COLD(11));
-                key = make_uint4(COLD_U(12), COLD_U(13), COLD_U(14), COLD_U(15));
-                depth = COLD_U(18);
+                key = path_key(prm.seed, COLD_U(14), COLD_U(12));
+                depth = COLD_U(15);
                 bool alive;
                 if (T.best.op < 0) {
                     L = L + Tp * C.background;                                  // renderer.rs:152-153
@@ -215,10 +215,10 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                     COLD(3) = ray.d.x; COLD(4) = ray.d.y; COLD(5) = ray.d.z;
                     COLD(6) = L.x; COLD(7) = L.y; COLD(8) = L.z;
                     COLD(9) = Tp.x; COLD(10) = Tp.y; COLD(11) = Tp.z;
-                    COLD_U(18) = depth;
+                    COLD_U(15) = depth;
                     start = true;
                 } else {
-                    red_add_f4(prm.sum + COLD_U(17), L.x, L.y, L.z, 1.0f);      // avg_color += new_color (renderer.rs:39)
+                    red_add_f4(prm.sum + COLD_U(14), L.x, L.y, L.z, 1.0f);      // avg_color += new_color (renderer.rs:39)
                     has_path = false;
                 }
             }
@@ -253,16 +253,17 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                         else { sv = idx / tile_n; pv = idx - sv * tile_n; ty_ = pv / tile_w; tx_ = pv - ty_ * tile_w; }
                         const int px = tile_x0 + tx_, py = tile_y0 + ty_;
                         const int pix = py * C.width + px;                       // renderer.rs:32-33
-                        key = path_key(prm.seed, (uint32_t)pix, (uint32_t)(prm.sample_begin + pool_sample0 + sv));
+                        const uint32_t sample = (uint32_t)(prm.sample_begin + pool_sample0 + sv);
+                        key = path_key(prm.seed, (uint32_t)pix, sample);
                         const Ray ray = camera_ray(C, px, py, key);
                         COLD(0) = ray.o.x; COLD(1) = ray.o.y; COLD(2) = ray.o.z;
                         COLD(3) = ray.d.x; COLD(4) = ray.d.y; COLD(5) = ray.d.z;
                         COLD(6) = 0.0f; COLD(7) = 0.0f; COLD(8) = 0.0f;
                         COLD(9) = 1.0f; COLD(10) = 1.0f; COLD(11) = 1.0f;
-                        COLD_U(12) = key.x; COLD_U(13) = key.y; COLD_U(14) = key.z; COLD_U(15) = key.w;
-                        COLD(16) = ray.time;
-                        COLD_U(17) = (uint32_t)pix;
-                        COLD_U(18) = 0u;
+                        COLD_U(12) = sample;
+                        COLD(13) = ray.time;
+                        COLD_U(14) = (uint32_t)pix;
+                        COLD_U(15) = 0u;
                         depth = 0u;
                         origin = -1;
                         has_path = true;
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                 Ray ray;
                 ray.o = f3(COLD(0), COLD(1), COLD(2));
                 ray.d = f3(COLD(3), COLD(4), COLD(5));
-                ray.time = COLD(16);
+                ray.time = COLD(13);
                 trav_begin(T, ray, 0, inf);
                 media_prepass(S, T, ray.time, tmin, key, depth);
                 if (COUNT) cnt[K_MEDIUM] += S.n_media;

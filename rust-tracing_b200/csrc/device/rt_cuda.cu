@@ -302,6 +302,8 @@ static render_fn v3_kernel(bool counting, int min_blocks) {
     switch (min_blocks) {
         case 8: return render_kernel_v3<false, 8>;
         case 7: return render_kernel_v3<false, 7>;
+        case 3: return render_kernel_v3<false, 3>;
+        case 2: return render_kernel_v3<false, 2>;
         case 6: return render_kernel_v3<false, 6>;
         case 5: return render_kernel_v3<false, 5>;
         default: return render_kernel_v3<false, 4>;
@@ -361,9 +363,9 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* e = std::getenv("RT_B200_SPHERE_REPS")) c->sphere_reps = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_NO_BOX")) c->box_primitives = std::atoi(e) == 0;
     if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
-    if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 4 ? v : 4; }
+    if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 2 ? v : 4; }
     CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    for (int mb : {4, 5, 6, 7, 8})
+    for (int mb : {2, 3, 4, 5, 6, 7, 8})
         CU(cudaFuncSetAttribute(v3_kernel(false, mb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     CU(cudaFuncSetAttribute(v3_kernel(true, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     int bps = 0;

@@ -7,9 +7,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SCENES = [(8, 800, 64, 0), (6, 600, 64, 50), (0, 400, 256, 50), (3, 800, 64, 0), (7, 600, 64, 0)]
-VARIANTS = [{"RT_B200_KERNEL": "1", "RT_B200_NO_BOX": "1"}, {"RT_B200_KERNEL": "1"}, {"RT_B200_KERNEL": "2"},
-            {"RT_B200_KERNEL": "2", "RT_B200_SHADE_MIN": "8"}, {"RT_B200_KERNEL": "2", "RT_B200_SHADE_MIN": "16"},
-            {"RT_B200_KERNEL": "2", "RT_B200_SHADE_MIN": "24"}]
+VARIANTS = [{}, {"RT_B200_KERNEL": "1"}, {"RT_B200_MIN_BLOCKS": "5"}, {"RT_B200_SHADE_MIN": "16"}, {"RT_B200_NO_BOX": "1"},
+            {"RT_B200_NO_HOIST": "1"}]
 if len(sys.argv) > 1:
     import json
     VARIANTS = json.loads(sys.argv[1])
