@@ -82,3 +82,19 @@ def test_no_cpu_fallback_without_gpu(rt):
     with pytest.raises(rt._abi.RtError) as e:
         rt.Context(0)
     assert e.value.status == rt._abi.RT_ERR_NO_DEVICE
+
+
+def test_cpp_mirror_header_builds_and_runs(rt, tmp_path):
+    """include/rt_b200.hpp (the C++ mirror of the crate's constructors) compiles standalone against the C ABI and the
+    example scene flattens; without a GPU the program stops at rt_context_create (no CPU fallback)."""
+    import subprocess
+    exe = str(tmp_path / "cornell")
+    csrc = os.path.join(ROOT, "rust-tracing_b200", "csrc")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "cornell.cpp"), "-L" + csrc, "-lrt_b200", "-Wl,-rpath," + csrc, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe, "2"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "25 hittables, 15 bvh nodes -> 56 stream words (7 inner, 6 quad, 2 box, 2 instance ops)" in out.stdout
+    assert ("no GPU" in out.stdout) or ("rendered 200x200" in out.stdout)
