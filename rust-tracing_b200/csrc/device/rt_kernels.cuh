@@ -662,7 +662,11 @@ __device__ __forceinline__ bool shade(const DevScene& S, const PerlinShared& P, 
         }
     }
     if (kind == RT_MAT_LAMBERTIAN || kind == RT_MAT_ISOTROPIC || kind == RT_MAT_DIFFUSE_LIGHT) {
-        const float3 c = texture_value(S, P, fbits(m0.y), h.p, h.u, h.v, h.uv_lazy, h.sn);
+        const int tex = fbits(m0.y);
+        const float4 t0 = __ldg(S.texs + 2 * tex);
+        // SolidColor (texture.rs:32-36) is by far the most common texture: answer it here, call out for the rest
+        const float3 c = fbits(t0.x) == RT_TEX_SOLID ? f3(__ldg(S.texs + 2 * tex + 1))
+                                                     : texture_value(S, P, tex, h.p, h.u, h.v, h.uv_lazy, h.sn);
         if (kind == RT_MAT_DIFFUSE_LIGHT) {   // emitted (both faces), no scatter: material.rs:114-122
             L = L + T * c;
             return false;
