@@ -311,6 +311,11 @@ typedef struct rt_render_stats {
 } rt_render_stats;
 int rt_render_get_stats(rt_context* ctx, rt_render_stats* out);
 
+/* Profiling runs only: with RT_B200_TIMING=1 in the environment at rt_context_create, every kernel launch of a render
+ * is bracketed by CUDA events on the launching stream. Returns the summed durations of the last render's shade and
+ * extend launches (render_v4.cuh) and the number of shade/extend iterations enqueued (all zero without timing). */
+int rt_render_get_kernel_times(rt_context* ctx, double* ms_shade, double* ms_extend, uint64_t* iterations);
+
 /* Instrumented run of the same kernel: counts the ops the device traversal executes (box tests, sphere tests,
  * quad tests, shades by material, ...) over the given sample range. counters[] receives the counts (returns how
  * many), *names_csv their comma-separated names. Used to state the device's own algorithmic flops per path. */

@@ -168,6 +168,7 @@ PROTOTYPES = {
     "rt_render": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp]),
     "rt_finalize_rgb8": (C.c_int, [vp, vp, C.c_int64, C.c_double, vp]),
     "rt_render_get_stats": (C.c_int, [vp, P(RenderStats)]),
+    "rt_render_get_kernel_times": (C.c_int, [vp, P(C.c_double), P(C.c_double), P(C.c_uint64)]),
     "rt_render_count_ops": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp, C.c_int, P(C.c_char_p)]),
     "rt_hit_batch": (C.c_int, [vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_uint64, vp]),
     "rt_texture_batch": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, vp]),

@@ -328,6 +328,12 @@ class Context:
         return {"paths": st.paths, "segments": st.segments, "kernel_launches": st.kernel_launches,
                 "last_kernel_ms": st.last_kernel_ms}
 
+    def kernel_times(self):
+        """Summed shade / extend launch durations of the last render (needs RT_B200_TIMING=1 at context creation)."""
+        a, b, n = C.c_double(), C.c_double(), C.c_uint64()
+        A.check(self._lib.rt_render_get_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return {"ms_shade": a.value, "ms_extend": b.value, "iterations": n.value}
+
     def count_ops(self, dscene, cam, sample_begin=0, sample_count=1, seed=0):
         """Op counts of the instrumented kernel over a sample range (dict name -> count)."""
         buf = np.zeros(64, dtype=np.uint64)

@@ -34,6 +34,11 @@ enum OpKind : uint32_t {
                          //   boundary xbox   : w1 = {a.xyz, sin} w2 = {b.xyz, cos} w3 = {min.xyz, 0} w4 = {max.xyz, 0}   size 5
     OP_BOX = 6,          // a Quad::cube list as ONE slab primitive: w0 = {min.xyz, hdr} w1 = {max.xyz, mat} w2 = {first_quad_prim_id, 0, 0, 0}  size 3
                          //   faces in quad.rs:45-93 order: 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y ; prim_id = first + face
+    OP_INNER_REF = 7,    // layout of OP_INNER, but the box is the reference's own node box and the test is aabb.rs:64-84 verbatim
+                         //   (per axis, never narrowed). Emitted for every BVH node - leaves included, bvh.rs:92 tests them too -
+                         //   whose subtree holds a quad that sticks out of its own bounding box: Quad::new boxes only the
+                         //   diagonal q .. q+u+v (quad.rs:41-43), so for a parallelogram that is not axis aligned the reference
+                         //   culls part of the quad, and which part depends on exactly this test. Tight culling would differ.
 };
 
 constexpr uint32_t FLAG_MOVING = 1u;   // sphere has center_vec
@@ -49,7 +54,8 @@ constexpr int kMaxHoistedMedia = 8;   // [Translate/RotateY chain of] a cube: en
 // before its words arrive lets the render kernel vote on what to run next without waiting for the load.
 inline uint32_t make_hdr(uint32_t kind, uint32_t flags = 0) { return kind | (flags << 4); }
 
-enum OpClass : uint32_t { CLS_SLAB = 0, CLS_SPHERE = 1, CLS_QUAD = 2, CLS_MEDIUM = 3, CLS_SHADE = 4, CLS_IDLE = 5 };
+enum OpClass : uint32_t { CLS_SLAB = 0, CLS_SPHERE = 1, CLS_QUAD = 2, CLS_MEDIUM = 3, CLS_SHADE = 4, CLS_IDLE = 5,
+                          CLS_BOX = 6 };   // OP_BOX as a class of its own (CompileOptions::box_class); otherwise it runs in the slab class
 inline uint32_t class_of_kind(uint32_t kind) {
     return kind == OP_SPHERE ? CLS_SPHERE : kind == OP_QUAD ? CLS_QUAD : kind == OP_MEDIUM ? CLS_MEDIUM : CLS_SLAB;
 }
@@ -78,6 +84,7 @@ struct CompiledScene {
 struct CompileOptions {
     bool box_primitives = true;   // false: emit cube lists as 6 quads (the reference's own structure), for A/B parity runs
     bool hoist_media = true;      // false: media stay in the op stream at their BVH position
+    bool box_class = false;       // true: OP_BOX lanes vote as CLS_BOX instead of diverging inside the slab class
 };
 
 // Returns 0 or a negative rt_status; message in *err.

@@ -20,7 +20,11 @@
 #pragma once
 
 
+#ifdef RT_OPT_SLAB_REPS
+constexpr int kSlabReps = RT_OPT_SLAB_REPS;
+#else
 constexpr int kSlabReps = 8;       // consecutive slab-class ops per vote (8 and 16 measured equal, 4 slower)
+#endif
 constexpr int kColdFields = 16;   // world o(3) d(3), L(3), Tp(3), sample index, time, pixel, depth (the RNG key is re-derived from pixel, sample)
 
 inline size_t v3_smem_bytes(int n_perlin) {
@@ -77,15 +81,26 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
             if (n_slab >= (unsigned)prm.slab_fast) {
                 pick = CLS_SLAB;
             } else {
+                // lanes per class: five 6-bit counters in one REDUX, plus a ballot for the box class
                 const unsigned tot = __reduce_add_sync(0xffffffffu, cls < CLS_IDLE ? (1u << (6 * cls)) : 0u);
-                if (tot == 0u) break;
+                const unsigned c_box = __popc(__ballot_sync(0xffffffffu, cls == CLS_BOX));
+                if (tot == 0u && c_box == 0u) break;
                 const unsigned c_sph = (tot >> 6) & 63u, c_quad = (tot >> 12) & 63u, c_med = (tot >> 18) & 63u, c_shade = (tot >> 24) & 63u;
-                unsigned best_n = n_slab;
-                pick = CLS_SLAB;
-                if (c_sph > best_n) { pick = CLS_SPHERE; best_n = c_sph; }
-                if (c_quad > best_n) { pick = CLS_QUAD; best_n = c_quad; }
-                if (c_med > best_n) { pick = CLS_MEDIUM; best_n = c_med; }
-                if ((c_shade > best_n && c_shade >= (unsigned)prm.shade_min) || best_n == 0u) pick = CLS_SHADE;
+                // a class that has gathered its quorum runs before the slab class gets the warp back; otherwise the
+                // most populated class runs (shading only with its quorum, or when nothing else can run)
+                if (c_shade >= (unsigned)prm.shade_min) pick = CLS_SHADE;
+                else if (c_sph >= (unsigned)prm.sphere_min) pick = CLS_SPHERE;
+                else if (c_box >= (unsigned)prm.box_min) pick = CLS_BOX;
+                else if (c_quad >= (unsigned)prm.quad_min) pick = CLS_QUAD;
+                else {
+                    unsigned best_n = n_slab;
+                    pick = CLS_SLAB;
+                    if (c_sph > best_n) { pick = CLS_SPHERE; best_n = c_sph; }
+                    if (c_box > best_n) { pick = CLS_BOX; best_n = c_box; }
+                    if (c_quad > best_n) { pick = CLS_QUAD; best_n = c_quad; }
+                    if (c_med > best_n) { pick = CLS_MEDIUM; best_n = c_med; }
+                    if (best_n == 0u) pick = CLS_SHADE;
+                }
             }
             if (COUNT) { if (lane == 0) cnt[K_VOTES]++; cnt[K_LANE_OPS] += (cls == pick); }
         }
@@ -124,7 +139,15 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                     }
                     FETCH_NEXT();
                 }
-                if (!__any_sync(0xffffffffu, cls == CLS_SLAB)) break;
+                if (__popc(__ballot_sync(0xffffffffu, cls == CLS_SLAB)) < (unsigned)prm.slab_exit) break;   // too few left: vote again
+            }
+        } else if (pick == CLS_BOX) {
+            if (cls == CLS_BOX) {        // OP_BOX as its own class (CompileOptions::box_class)
+                if (COUNT) cnt[K_BOX]++;
+                const float tb = T.best.t;
+                cls = op_slab_class(S, T, w0, w1, tmin, origin);
+                if (COUNT && T.best.t != tb) cnt[K_BOX_HIT]++;
+                FETCH_NEXT();
             }
         } else if (pick == CLS_SPHERE) {
 #pragma unroll 1

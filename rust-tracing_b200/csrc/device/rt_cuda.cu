@@ -49,6 +49,8 @@ struct RenderParams {
     int shade_min;               // the shade class may win the vote once this many lanes wait for it
     int slab_fast;               // v3: lanes in the slab class that skip the full vote
     int slab_reps, sphere_reps;  // v3: consecutive ops a class may run per vote (slab: compile-time kSlabReps)
+    int slab_exit;               // v3: the slab repetitions stop (and the warp votes again) once fewer lanes than this remain in the class
+    int sphere_min, box_min, quad_min;   // v3: quorum at which a minority class runs ahead of the slab class
 };
 
 // op counters of the instrumented kernel (rt_render_count_ops): what the device traversal actually executes
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
 }
 
 #include "render_v3.cuh"
+#include "render_v4.cuh"
 
 struct DevRayIn { float ox, oy, oz, dx, dy, dz, time, pad; };
 struct DevHitOut { float t, px, py, pz, nx, ny, nz, u, v; int hit, front_face, prim, mat; };
@@ -310,17 +313,56 @@ static render_fn v3_kernel(bool counting, int min_blocks) {
     }
 }
 
+typedef void (*wf_extend_fn)(const WfParams);
+typedef void (*wf_shade_fn)(const WfParams, const int);
+static wf_extend_fn wf_extend(int min_blocks) {
+    switch (min_blocks) {
+        case 12: return wf_extend_kernel<12>;
+        case 10: return wf_extend_kernel<10>;
+        case 6: return wf_extend_kernel<6>;
+        case 5: return wf_extend_kernel<5>;
+        case 4: return wf_extend_kernel<4>;
+        default: return wf_extend_kernel<8>;
+    }
+}
+static wf_shade_fn wf_shade(int min_blocks) {
+    switch (min_blocks) {
+        case 8: return wf_shade_kernel<8>;
+        case 6: return wf_shade_kernel<6>;
+        case 3: return wf_shade_kernel<3>;
+        default: return wf_shade_kernel<4>;
+    }
+}
+constexpr int kWfBatch = 16;   // iterations enqueued between two looks at the live flag
+
 struct rt_context {
+    // wavefront renderer (render_v4.cuh): pool of in-flight paths and its bookkeeping
+    WavePool pool{};
+    size_t pool_capacity = 0;
+    int pool_slots = 1 << 20;    // 5 x 16 B per slot = 80 MB: stays in the 126 MB L2 between the two kernels
+    int wf_extend_blocks = 8, wf_shade_blocks = 4, wf_fetch_min = 6, wf_slab_fast = 14;
+    unsigned long long* d_path_counter = nullptr;
+    unsigned int* d_slot_cursor = nullptr;
+    unsigned int* d_live = nullptr;          // 2 x kWfBatch flags
+    unsigned int* h_live = nullptr;          // pinned, 2 flags
+    ulonglong2* d_reserve = nullptr;
+    size_t reserve_warps = 0;
+    cudaEvent_t wf_event[2] = {nullptr, nullptr};
+    bool timing = false;                     // RT_B200_TIMING: CUDA events around every launch (profiling runs only)
+    double ms_extend = 0.0, ms_shade = 0.0;  // of the last render, timing mode only
+    uint64_t wf_iterations = 0;
     int device = 0;
     int sm_count = 0;
     int clock_khz = 0;
     size_t total_mem = 0;
     int blocks_per_sm = 1;       // of the selected production kernel
-    int variant = 3;             // 3: render_v3.cuh (product); 1: whole-segment-per-iteration loop (kept for A/B runs)
+    int variant = 3;             // 4: wavefront (render_v4.cuh); 3: megakernel (render_v3.cuh); 1: whole-segment loop (A/B only)
     int min_blocks = 6;          // occupancy variant: resident 128-thread blocks per SM the kernel is compiled for
     bool hoist_media = true;
     int shade_min = 24;
     int slab_fast = 14, slab_reps = 8, sphere_reps = 2;
+    int slab_exit = 1, sphere_min = 33, box_min = 33, quad_min = 33;
+    bool box_class = false;
     bool box_primitives = true;
     unsigned int* d_counter = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -356,18 +398,35 @@ int rt_context_create(int device_id, rt_context** out) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
     c->clock_khz = khz;
     // development switches (A/B runs; the defaults are the product)
-    if (const char* e = std::getenv("RT_B200_KERNEL")) c->variant = std::atoi(e) == 1 ? 1 : 3;
+    if (const char* e = std::getenv("RT_B200_KERNEL")) { const int v = std::atoi(e); c->variant = v == 1 ? 1 : v == 4 ? 4 : 3; }
+    if (const char* e = std::getenv("RT_B200_POOL")) c->pool_slots = std::max(1024, std::atoi(e)) / 32 * 32;
+    if (const char* e = std::getenv("RT_B200_WF_EXTEND_BLOCKS")) c->wf_extend_blocks = std::atoi(e);
+    if (const char* e = std::getenv("RT_B200_WF_SHADE_BLOCKS")) c->wf_shade_blocks = std::atoi(e);
+    if (const char* e = std::getenv("RT_B200_WF_FETCH_MIN")) c->wf_fetch_min = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_WF_SLAB_FAST")) c->wf_slab_fast = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_TIMING")) c->timing = std::atoi(e) != 0;
     if (const char* e = std::getenv("RT_B200_SHADE_MIN")) c->shade_min = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_SLAB_FAST")) c->slab_fast = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_SLAB_REPS")) c->slab_reps = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_SPHERE_REPS")) c->sphere_reps = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_NO_BOX")) c->box_primitives = std::atoi(e) == 0;
+    if (const char* e = std::getenv("RT_B200_SLAB_EXIT")) c->slab_exit = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_SPHERE_MIN")) c->sphere_min = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_BOX_MIN")) c->box_min = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_QUAD_MIN")) c->quad_min = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RT_B200_BOX_CLASS")) c->box_class = std::atoi(e) != 0;
     if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
     if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 2 ? v : 4; }
     CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
     for (int mb : {2, 3, 4, 5, 6, 7, 8})
         CU(cudaFuncSetAttribute(v3_kernel(false, mb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     CU(cudaFuncSetAttribute(v3_kernel(true, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
+    CU(cudaMalloc(&c->d_path_counter, sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_slot_cursor, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_live, 2 * kWfBatch * sizeof(unsigned int)));
+    CU(cudaMallocHost(&c->h_live, 2 * sizeof(unsigned int)));
+    CU(cudaEventCreateWithFlags(&c->wf_event[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->wf_event[1], cudaEventDisableTiming));
     int bps = 0;
     if (c->variant == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_kernel, kBlockThreads, perlin_smem_bytes()));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v3_kernel(false, c->min_blocks), kBlockThreads, v3_smem_bytes(1)));
@@ -385,6 +444,10 @@ void rt_context_destroy(rt_context* c) {
     cudaFree(c->d_counter);
     cudaFree(c->d_stats);
     cudaFree(c->d_fb);
+    cudaFree(c->pool.ray0); cudaFree(c->pool.ray1); cudaFree(c->pool.hit); cudaFree(c->pool.st0); cudaFree(c->pool.st1);
+    cudaFree(c->d_path_counter); cudaFree(c->d_slot_cursor); cudaFree(c->d_live); cudaFree(c->d_reserve);
+    if (c->h_live) cudaFreeHost(c->h_live);
+    for (cudaEvent_t e : c->wf_event) if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -414,6 +477,7 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     CompileOptions copt;
     copt.box_primitives = c->box_primitives;
     copt.hoist_media = c->hoist_media;
+    copt.box_class = c->box_class && c->variant == 3;
     int rc = compile_scene(desc, copt, &s->compiled, &err);
     if (rc < 0) { delete s; return fail(rc, err ? err : "compile_scene failed"); }
     if (s->compiled.n_perlin > kMaxPerlinShared) { delete s; return fail(RT_ERR_UNSUPPORTED, "more than 4 NoiseTexture tables in one scene"); }
@@ -486,7 +550,7 @@ int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out) {
         std::memcpy(&hdr, &cs.ops[i].w, 4);
         const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
         switch (kind) {
-            case OP_INNER: out->n_inner++; i += 2; break;
+            case OP_INNER: case OP_INNER_REF: out->n_inner++; i += 2; break;
             case OP_SPHERE: out->n_sphere++; i += (flags & FLAG_MOVING) ? 3 : 2; break;
             case OP_QUAD: out->n_quad++; i += 4; break;
             case OP_XFORM_ENTER: out->n_xform++; i += 4; break;
@@ -513,8 +577,131 @@ void rt_scene_destroy(rt_scene* s) {
     delete s;
 }
 
+// Wavefront render (render_v4.cuh): alternate wf_shade_kernel / wf_extend_kernel over the pool until no slot carries
+// a ray. Iterations are enqueued in batches of kWfBatch; the live flag of batch b is looked at after batch b + 1 has
+// been enqueued, so the stream never runs dry while the host decides. Returns with the stream drained.
+static size_t wf_shade_smem(int n_perlin) {
+    const int np = n_perlin < kMaxPerlinShared ? n_perlin : kMaxPerlinShared;
+    return (size_t)np * (256 * sizeof(float4) + 768);
+}
+
+static int wf_ensure_pool(rt_context* c, size_t slots) {
+    if (c->pool_capacity >= slots) return RT_OK;
+    cudaFree(c->pool.ray0); cudaFree(c->pool.ray1); cudaFree(c->pool.hit); cudaFree(c->pool.st0); cudaFree(c->pool.st1);
+    c->pool = WavePool{};
+    c->pool_capacity = 0;
+    CU(cudaMalloc(&c->pool.ray0, slots * sizeof(float4)));
+    CU(cudaMalloc(&c->pool.ray1, slots * sizeof(float4)));
+    CU(cudaMalloc(&c->pool.hit, slots * sizeof(float4)));
+    CU(cudaMalloc(&c->pool.st0, slots * sizeof(float4)));
+    CU(cudaMalloc(&c->pool.st1, slots * sizeof(float4)));
+    c->pool_capacity = slots;
+    return RT_OK;
+}
+
+static int launch_render_v4(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
+                            int64_t sample_count, uint64_t seed, void* d_sum_rgba, cudaStream_t stream) {
+    WfParams prm;
+    prm.scene = s->dev;
+    prm.cam = make_dev_camera(*cam);
+    prm.seed = seed;
+    prm.sample_begin = sample_begin;
+    prm.n_pixels = (uint32_t)((int64_t)prm.cam.width * prm.cam.height);
+    prm.n_paths = (unsigned long long)prm.n_pixels * (unsigned long long)sample_count;
+    prm.tiled = (prm.cam.width % kTileW == 0 && prm.cam.height % kTileH == 0) ? 1 : 0;
+    prm.tiles_x = prm.cam.width / kTileW;
+    size_t slots = (size_t)c->pool_slots;
+    const unsigned long long rounded = (prm.n_paths + 31ull) / 32ull * 32ull;
+    if (rounded < (unsigned long long)slots) slots = (size_t)rounded;
+    int rc = wf_ensure_pool(c, slots);
+    if (rc < 0) return rc;
+    prm.pool = c->pool;
+    prm.pool.n_slots = (int)slots;
+    prm.sum = static_cast<float4*>(d_sum_rgba);
+    prm.path_counter = c->d_path_counter;
+    prm.slot_cursor = c->d_slot_cursor;
+    prm.stats = c->d_stats;
+    prm.first_class = (int)s->compiled.first_class;
+    prm.fetch_min = c->wf_fetch_min;
+    prm.slab_fast = c->wf_slab_fast;
+    prm.sphere_reps = c->sphere_reps;
+    prm.slab_exit = c->slab_exit;
+    prm.sphere_min = c->sphere_min;
+
+    wf_extend_fn extend = wf_extend(c->wf_extend_blocks);
+    wf_shade_fn shade_k = wf_shade(c->wf_shade_blocks);
+    const size_t smem = wf_shade_smem(s->dev.n_perlin);
+    int bps_e = 1, bps_s = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_e, extend, kBlockThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_s, shade_k, kWfShadeThreads, smem));
+    const size_t slot_warps = slots / 32;
+    size_t grid_e = (size_t)c->sm_count * (size_t)std::max(1, bps_e);
+    size_t grid_s = (size_t)c->sm_count * (size_t)std::max(1, bps_s);
+    grid_e = std::max<size_t>(1, std::min(grid_e, (slot_warps + kBlockThreads / 32 - 1) / (kBlockThreads / 32)));
+    grid_s = std::max<size_t>(1, std::min(grid_s, (slot_warps + kWfShadeThreads / 32 - 1) / (kWfShadeThreads / 32)));
+    const size_t shade_warps = grid_s * (kWfShadeThreads / 32);
+    if (c->reserve_warps < shade_warps) {
+        cudaFree(c->d_reserve);
+        c->d_reserve = nullptr;
+        c->reserve_warps = 0;
+        CU(cudaMalloc(&c->d_reserve, shade_warps * sizeof(ulonglong2)));
+        c->reserve_warps = shade_warps;
+    }
+    prm.reserve = c->d_reserve;
+
+    CU(cudaMemsetAsync(c->d_path_counter, 0, sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(c->d_slot_cursor, 0, sizeof(unsigned int), stream));
+    CU(cudaMemsetAsync(c->d_reserve, 0, shade_warps * sizeof(ulonglong2), stream));
+    CU(cudaMemsetAsync(c->d_stats, 0, K_NUM * sizeof(unsigned long long), stream));
+    wf_init_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(prm.pool.hit, (int)slots);
+    c->launches += 1;
+    c->ms_extend = c->ms_shade = 0.0;
+    c->wf_iterations = 0;
+
+    std::vector<cudaEvent_t> tev;   // timing mode: begin / middle / end of every iteration
+    for (int b = 0;; ++b) {
+        unsigned int* live = c->d_live + (b & 1) * kWfBatch;
+        prm.live_flag = live;
+        CU(cudaMemsetAsync(live, 0, kWfBatch * sizeof(unsigned int), stream));
+        for (int k = 0; k < kWfBatch; ++k) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+            if (c->timing) {
+                cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+                tev.push_back(e0); tev.push_back(e1); tev.push_back(e2);
+                cudaEventRecord(e0, stream);
+            }
+            shade_k<<<(unsigned)grid_s, kWfShadeThreads, smem, stream>>>(prm, k);
+            if (c->timing) cudaEventRecord(e1, stream);
+            extend<<<(unsigned)grid_e, kBlockThreads, 0, stream>>>(prm);
+            if (c->timing) cudaEventRecord(e2, stream);
+        }
+        CU(cudaGetLastError());
+        c->launches += 2 * kWfBatch;
+        c->wf_iterations += kWfBatch;
+        CU(cudaMemcpyAsync(c->h_live + (b & 1), live + (kWfBatch - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(c->wf_event[b & 1], stream));
+        if (b >= 1) {
+            CU(cudaEventSynchronize(c->wf_event[(b - 1) & 1]));
+            if (c->h_live[(b - 1) & 1] == 0u) break;
+        }
+    }
+    CU(cudaStreamSynchronize(stream));
+    if (c->timing) {
+        for (size_t k = 0; k + 2 < tev.size(); k += 3) {
+            float a = 0.0f, b2 = 0.0f;
+            cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
+            cudaEventElapsedTime(&b2, tev[k + 1], tev[k + 2]);
+            c->ms_shade += a;
+            c->ms_extend += b2;
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
+    return RT_OK;
+}
+
 static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
                          int64_t sample_count, uint64_t seed, void* d_sum_rgba, cudaStream_t stream, bool counting) {
+    if (c->variant == 4 && !counting) return launch_render_v4(c, s, cam, sample_begin, sample_count, seed, d_sum_rgba, stream);
     RenderParams prm;
     prm.scene = s->dev;
     prm.cam = make_dev_camera(*cam);
@@ -541,6 +728,10 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     prm.slab_fast = c->slab_fast;
     prm.slab_reps = c->slab_reps;
     prm.sphere_reps = c->sphere_reps;
+    prm.slab_exit = c->slab_exit;
+    prm.sphere_min = c->sphere_min;
+    prm.box_min = c->box_min;
+    prm.quad_min = c->quad_min;
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), stream));
     CU(cudaMemsetAsync(c->d_stats, 0, K_NUM * sizeof(unsigned long long), stream));
     int grid = c->sm_count * c->blocks_per_sm;
@@ -609,6 +800,14 @@ int rt_render_get_stats(rt_context* c, rt_render_stats* out) {
     out->segments = h[1];
     out->kernel_launches = c->launches;
     out->last_kernel_ms = 0.0f;
+    return RT_OK;
+}
+
+int rt_render_get_kernel_times(rt_context* c, double* ms_shade, double* ms_extend, uint64_t* iterations) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_get_kernel_times: context is null");
+    if (ms_shade) *ms_shade = c->ms_shade;
+    if (ms_extend) *ms_extend = c->ms_extend;
+    if (iterations) *iterations = c->wf_iterations;
     return RT_OK;
 }
 

@@ -141,6 +141,20 @@ __device__ __forceinline__ bool slab(float4 w0, float4 w1, float3 o, float3 inv,
     return te <= tx * 1.0000012f + 1e-30f || te <= tx;
 }
 
+// AABB::hit exactly as aabb.rs:64-84 states it: every axis is tested against the ORIGINAL interval, the interval is
+// never narrowed between axes. Used only for OP_INNER_REF nodes (dev_scene.h), where the outcome of this very test
+// decides which part of a quad the reference can see.
+__device__ __forceinline__ bool aabb_hit_reference(float4 w0, float4 w1, float3 o, float3 inv, float tmin, float tmax) {
+    const float ax = (w0.x - o.x) * inv.x, bx = (w1.x - o.x) * inv.x;
+    const float ay = (w0.y - o.y) * inv.y, by = (w1.y - o.y) * inv.y;
+    const float az = (w0.z - o.z) * inv.z, bz = (w1.z - o.z) * inv.z;
+    const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+    const bool mx = fminf(sx ? ax : bx, tmax) <= fmaxf(sx ? bx : ax, tmin);   // t_max <= t_min -> miss (aabb.rs:79-81)
+    const bool my = fminf(sy ? ay : by, tmax) <= fmaxf(sy ? by : ay, tmin);
+    const bool mz = fminf(sz ? az : bz, tmax) <= fmaxf(sz ? bz : az, tmin);
+    return !(mx || my || mz);
+}
+
 // local = R(x - a) + b with R = rotate-y as in hittable.rs:164-168
 __device__ __forceinline__ float3 xform_point(float3 x, float4 w2, float4 w3) {
     const float3 q = x - f3(w2);
@@ -210,6 +224,9 @@ __device__ __noinline__ bool sphere_roots_f64(float3 o, float3 d, float time, co
 
 __device__ __forceinline__ void op_inner(Trav& T, float4 w0, float4 w1, float tmin) {
     T.i = slab(w0, w1, T.o, T.inv, tmin, T.best.t) ? T.i + 2 : fbits(w1.w);
+}
+__device__ __forceinline__ void op_inner_ref(Trav& T, float4 w0, float4 w1, float tmin) {
+    T.i = aabb_hit_reference(w0, w1, T.o, T.inv, tmin, T.best.t) ? T.i + 2 : fbits(w1.w);
 }
 
 __device__ __forceinline__ void op_sphere(const DevScene& S, Trav& T, float4 w0, float4 w1, float time, float tmin, int origin) {
@@ -304,6 +321,11 @@ __device__ __forceinline__ uint32_t op_slab_class(const DevScene& S, Trav& T, fl
     const uint32_t kind = hdr & 15u;
     const uint32_t ft = (hdr >> 8) & 7u, sk = (hdr >> 11) & 7u;
     if (kind == OP_XFORM_EXIT) { op_xform_exit(T); return ft; }
+    if (kind == OP_INNER_REF) {
+        const bool pass = aabb_hit_reference(w0, w1, T.o, T.inv, tmin, T.best.t);
+        T.i = pass ? T.i + 2 : fbits(w1.w);
+        return pass ? ft : sk;
+    }
     float te, tx;
     slab_interval(w0, w1, T.o, T.inv, &te, &tx);
     if (kind == OP_BOX) {
@@ -417,6 +439,7 @@ __device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, 
         const float4 w1 = __ldg(ops + T.i + 1);
         const uint32_t kind = (uint32_t)fbits(w0.w) & 15u;
         if (kind == OP_INNER) op_inner(T, w0, w1, tmin);
+        else if (kind == OP_INNER_REF) op_inner_ref(T, w0, w1, tmin);
         else if (kind == OP_SPHERE) op_sphere(S, T, w0, w1, ray.time, tmin, origin);
         else if (kind == OP_BOX) op_box(T, w0, w1, tmin, origin);
         else if (kind == OP_QUAD) op_quad(S, T, w0, w1, tmin, origin);

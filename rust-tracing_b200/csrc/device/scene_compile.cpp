@@ -61,6 +61,7 @@ struct Compiler {
     std::vector<Box> tight_hittable;  // memo, by hittable id
     std::vector<Box> tight_node;      // memo, by bvh node index
     std::vector<char> have_h, have_n;
+    std::vector<signed char> loose_h, loose_n;   // -1 unknown, 0 / 1: subtree holds a quad that sticks out of its own box
     double scale = 1.0;
     std::vector<F4> hoisted;             // bodies of world-space media (appended after the world program)
     std::vector<int32_t> hoisted_at;     // offsets into `hoisted`
@@ -68,6 +69,45 @@ struct Compiler {
     bool fail(int code, const std::string& m) {
         if (status == 0) { status = code; err = m; }
         return false;
+    }
+
+    // Quad::new boxes the diagonal q .. q+u+v only (quad.rs:41-43): a parallelogram that is not axis aligned sticks
+    // out of its own bounding box.
+    static void quad_corners(const rt_hittable_desc& h, double c[4][3]) {
+        for (int k = 0; k < 3; ++k) {
+            c[0][k] = h.v0[k]; c[1][k] = h.v0[k] + h.v1[k]; c[2][k] = h.v0[k] + h.v2[k]; c[3][k] = h.v0[k] + h.v1[k] + h.v2[k];
+        }
+    }
+    bool loose_quad(const rt_hittable_desc& h) const {
+        double c[4][3];
+        quad_corners(h, c);
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 3; ++k) {
+                const double eps = 1e-9 * std::fmax(1.0, std::fabs(c[i][k]));
+                if (c[i][k] < h.bbox[2 * k] - eps || c[i][k] > h.bbox[2 * k + 1] + eps) return true;
+            }
+        return false;
+    }
+    bool loose(int id) {
+        if (loose_h[id] >= 0) return loose_h[id] != 0;
+        const rt_hittable_desc& h = d->hittables[id];
+        bool l = false;
+        switch (h.kind) {
+            case RT_HIT_QUAD: l = loose_quad(h); break;
+            case RT_HIT_LIST: for (int i = 0; i < h.count && !l; ++i) l = loose(d->list_items[h.child + i]); break;
+            case RT_HIT_TRANSLATE: case RT_HIT_ROTATE_Y: case RT_HIT_CONSTANT_MEDIUM: l = loose(h.child); break;
+            case RT_HIT_BVH: l = loose_node(h.child); break;
+            default: break;
+        }
+        loose_h[id] = l ? 1 : 0;
+        return l;
+    }
+    bool loose_node(int n) {
+        if (loose_n[n] >= 0) return loose_n[n] != 0;
+        const rt_bvh_node_desc& node = d->bvh_nodes[n];
+        const bool l = node.object >= 0 ? loose(node.object) : (loose_node(node.left) || loose_node(node.right));
+        loose_n[n] = l ? 1 : 0;
+        return l;
     }
 
     // Tight bounds of the geometry in the hittable's own (outer) space. The reference's list boxes
@@ -83,6 +123,12 @@ struct Compiler {
             case RT_HIT_QUAD:
                 b.valid = true;
                 for (int c = 0; c < 3; ++c) { b.lo[c] = h.bbox[2 * c]; b.hi[c] = h.bbox[2 * c + 1]; }
+                if (h.kind == RT_HIT_QUAD && loose_quad(h)) {   // the boxes the device adds (lists, instances, media) must hold all of it
+                    double q[4][3];
+                    quad_corners(h, q);
+                    for (int i = 0; i < 4; ++i)
+                        for (int c = 0; c < 3; ++c) { b.lo[c] = std::fmin(b.lo[c], q[i][c]); b.hi[c] = std::fmax(b.hi[c], q[i][c]); }
+                }
                 break;
             case RT_HIT_LIST:
                 for (int i = 0; i < h.count; ++i) b = box_union(b, tight(d->list_items[h.child + i]));
@@ -229,6 +275,16 @@ struct Compiler {
 
     void emit_node(int n, bool in_boundary) {
         const rt_bvh_node_desc& node = d->bvh_nodes[n];
+        if (loose_node(n)) {   // the reference's own box and test, at every node of the path down to the loose quad (dev_scene.h)
+            Box rb;
+            rb.valid = true;
+            for (int c = 0; c < 3; ++c) { rb.lo[c] = node.bbox[2 * c]; rb.hi[c] = node.bbox[2 * c + 1]; }
+            const int w1 = push_box_header(rb, make_hdr(OP_INNER_REF));
+            if (node.object >= 0) emit(node.object, in_boundary);
+            else { emit_node(node.left, in_boundary); emit_node(node.right, in_boundary); }
+            patch_skip(w1);
+            return;
+        }
         if (node.object >= 0) { emit(node.object, in_boundary); return; }
         const int w1 = push_box_header(tight_of_node(n), make_hdr(OP_INNER));
         emit_node(node.left, in_boundary);
@@ -353,6 +409,8 @@ int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, Compiled
     c.have_h.assign(desc->n_hittables, 0);
     c.tight_node.resize(desc->n_bvh_nodes);
     c.have_n.assign(desc->n_bvh_nodes, 0);
+    c.loose_h.assign(desc->n_hittables, -1);
+    c.loose_n.assign(desc->n_bvh_nodes, -1);
 
     // validate references once so the emitters can index freely
     for (int i = 0; i < desc->n_hittables && !c.status; ++i) {
@@ -417,14 +475,18 @@ int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, Compiled
         const int n = (int)ops.size();
         auto hdr_of = [&](int i) { uint32_t u; std::memcpy(&u, &ops[i].w, 4); return u; };
         auto int_of = [&](float f) { int32_t v; std::memcpy(&v, &f, 4); return v; };
-        auto cls_at = [&](int i) -> uint32_t { return i >= n ? (uint32_t)CLS_SHADE : class_of_kind(hdr_of(i) & 15u); };
+        auto cls_at = [&](int i) -> uint32_t {
+            if (i >= n) return (uint32_t)CLS_SHADE;
+            const uint32_t kind = hdr_of(i) & 15u;
+            return kind == OP_BOX && opt.box_class ? (uint32_t)CLS_BOX : class_of_kind(kind);
+        };
         int i = 0;
         while (i < n) {
             const uint32_t hdr = hdr_of(i);
             const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
             int size = 2, skip = -1;
             switch (kind) {
-                case OP_INNER: size = 2; skip = int_of(ops[i + 1].w); break;
+                case OP_INNER: case OP_INNER_REF: size = 2; skip = int_of(ops[i + 1].w); break;
                 case OP_SPHERE: size = (flags & FLAG_MOVING) ? 3 : 2; break;
                 case OP_QUAD: size = 4; break;
                 case OP_XFORM_ENTER: size = 4; skip = int_of(ops[i + 1].w); break;

@@ -217,3 +217,25 @@ def test_hit_parity_one_million_rays(rt, ob, ctx, earth, idx):
     stats = check_hits(dev, ref, rays, max_inequivalent=64)
     assert stats["flips"] <= 8
     ds.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_hit_parity_random_scenes(rt, ob, ctx, seed):
+    """Generated scenes (tools/fuzz_scenes.py): quads with arbitrary edge vectors, nested BVHs, instances, media. A quad
+    that is not axis aligned sticks out of the box Quad::new gives it (quad.rs:41-43: the diagonal q .. q+u+v only), so
+    inside a BVH the reference sees just the part its own per-axis box test (aabb.rs:64-84) lets through - the device
+    must reproduce that, not the geometrically complete quad (OP_INNER_REF, dev_scene.h)."""
+    from fuzz_scenes import random_scene
+    s = random_scene(1000 + seed)
+    ds = ctx.upload(s)
+    rng = np.random.default_rng(seed)
+    n = 1 << 15
+    rays = np.zeros(n, dtype=rt._abi.ray_dtype())
+    rays["origin"] = rng.uniform(-14, 14, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.5, 2, (n, 1))
+    rays["time"] = rng.random(n)
+    ref = ob.hit_batch(s.desc, rays, seed=seed)
+    dev = ctx.hit_batch(ds, rays, seed=seed)
+    check_hits(dev, ref, rays, max_inequivalent=6)
+    ds.close()

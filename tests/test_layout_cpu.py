@@ -36,6 +36,22 @@ def test_degenerate_cube_keeps_its_quads(rt):
     assert L["n_box"] == 0 and L["n_quad"] == 6
 
 
+def test_quads_that_stick_out_of_their_box_get_reference_nodes(rt):
+    """Quad::new boxes the diagonal q .. q+u+v only (quad.rs:41-43). For such a quad every BVH node above it, its own
+    leaf included, is emitted with the reference's box and per-axis test (OP_INNER_REF) instead of a tight box."""
+    def layout(skew):
+        s = rt.Scene(bvh_seed=5)
+        m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))
+        l = rt.HittableList()
+        l.add(s.Quad((0, 0, 0), (1, 0, 0.5 * skew), (0, 1, -0.5 * skew), m))
+        l.add(s.Quad((3, 0, 0), (1, 0, 0), (0, 1, 0), m))
+        l.add(s.Sphere((6, 0, 0), 0.5, m))
+        s.finish(s.BVHNode(l))
+        return rt.scene_layout(s)
+    assert layout(0)["n_inner"] == 2          # root + one branch; leaves need no box of their own
+    assert layout(1)["n_inner"] == 3          # + the leaf box of the skewed quad
+
+
 def test_media_inside_instances_stay_in_the_stream(rt):
     s = rt.Scene()
     m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))

@@ -15,6 +15,8 @@ if len(sys.argv) > 1:
 if len(sys.argv) > 2:
     keep = [int(x) for x in sys.argv[2].split(",")]
     SCENES = [s for s in SCENES if s[0] in keep]
+if len(sys.argv) > 3:      # spp override
+    SCENES = [(a, b, int(sys.argv[3]), d) for a, b, _, d in SCENES]
 for var in VARIANTS:
     for scene, width, spp, depth in SCENES:
         env = dict(os.environ, **var)
