@@ -284,6 +284,13 @@ typedef struct rt_layout_info {
 } rt_layout_info;
 int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out);
 
+/* The flattened traversal stream itself, as rt_scene_upload would place it in HBM (host dry run, no GPU): float4
+ * words (4 floats each; headers and links are integers stored bit-for-bit), the world program in [0, n_world_words),
+ * hoisted media bodies behind it. words may be NULL to query *n_total_words. media_ops receives the word indices of
+ * the hoisted media (capacity 8). Lets a host-side check walk exactly what the kernels walk (tests/opstream.py). */
+int rt_scene_ops_export(const rt_scene_desc* desc, float* words, int64_t capacity_words, int64_t* n_total_words,
+                        int32_t* n_world_words, int32_t* media_ops, int32_t* n_media, int32_t* first_class);
+
 /* Render samples [sample_begin, sample_begin+sample_count) of every pixel and ADD the
  * per-pixel sums into a device float4 buffer (x,y,z = radiance sum, w = sample count),
  * W*H elements row-major (pos = j*W + i, renderer.rs:32-33). Asynchronous on `stream`

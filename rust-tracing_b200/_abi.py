@@ -164,6 +164,8 @@ PROTOTYPES = {
     "rt_scene_upload": (C.c_int, [vp, P(SceneDesc), P(vp)]),
     "rt_scene_destroy": (None, [vp]),
     "rt_scene_layout": (C.c_int, [P(SceneDesc), P(LayoutInfo)]),
+    "rt_scene_ops_export": (C.c_int, [P(SceneDesc), P(C.c_float), C.c_int64, P(C.c_int64), P(C.c_int32), P(C.c_int32),
+                                      P(C.c_int32), P(C.c_int32)]),
     "rt_render_accumulate": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp, vp]),
     "rt_render": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp]),
     "rt_finalize_rgb8": (C.c_int, [vp, vp, C.c_int64, C.c_double, vp]),

@@ -253,6 +253,20 @@ def scene_layout(scene):
     return {name: getattr(info, name) for name, _ in A.LayoutInfo._fields_}
 
 
+def scene_ops(scene):
+    """rt_scene_ops_export: the flattened traversal stream (host dry run). Returns a dict with `words` (float32 (N, 4)),
+    `n_world_words`, `media_ops` (word indices of the hoisted media) and `first_class`."""
+    lib = A.lib()
+    n, nw, nm, fc = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+    media = (C.c_int32 * 8)()
+    A.check(lib.rt_scene_ops_export(C.byref(scene.desc), None, 0, C.byref(n), None, None, None, None))
+    words = np.zeros((n.value, 4), dtype=np.float32)
+    A.check(lib.rt_scene_ops_export(C.byref(scene.desc), words.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n),
+                                    C.byref(nw), media, C.byref(nm), C.byref(fc)))
+    return {"words": words, "n_world_words": nw.value, "media_ops": [int(media[k]) for k in range(nm.value)],
+            "first_class": fc.value}
+
+
 class DeviceScene:
     def __init__(self, ctx, scene):
         self.ctx = ctx

@@ -85,6 +85,7 @@ struct CompileOptions {
     bool box_primitives = true;   // false: emit cube lists as 6 quads (the reference's own structure), for A/B parity runs
     bool hoist_media = true;      // false: media stay in the op stream at their BVH position
     bool box_class = false;       // true: OP_BOX lanes vote as CLS_BOX instead of diverging inside the slab class
+    bool prune_boxes = true;      // drop cull boxes (OP_INNER) that cost more tests than they save (scene_compile.cpp, prune_stream)
 };
 
 // Returns 0 or a negative rt_status; message in *err.

@@ -363,6 +363,7 @@ struct rt_context {
     int slab_fast = 14, slab_reps = 8, sphere_reps = 2;
     int slab_exit = 1, sphere_min = 33, box_min = 33, quad_min = 33;
     bool box_class = false;
+    bool prune_boxes = true;
     bool box_primitives = true;
     unsigned int* d_counter = nullptr;
     unsigned long long* d_stats = nullptr;
@@ -415,6 +416,7 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* e = std::getenv("RT_B200_BOX_MIN")) c->box_min = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_QUAD_MIN")) c->quad_min = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_BOX_CLASS")) c->box_class = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RT_B200_NO_PRUNE")) c->prune_boxes = std::atoi(e) == 0;
     if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
     if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 2 ? v : 4; }
     CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
@@ -478,6 +480,7 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     copt.box_primitives = c->box_primitives;
     copt.hoist_media = c->hoist_media;
     copt.box_class = c->box_class && c->variant == 3;
+    copt.prune_boxes = c->prune_boxes;
     int rc = compile_scene(desc, copt, &s->compiled, &err);
     if (rc < 0) { delete s; return fail(rc, err ? err : "compile_scene failed"); }
     if (s->compiled.n_perlin > kMaxPerlinShared) { delete s; return fail(RT_ERR_UNSUPPORTED, "more than 4 NoiseTexture tables in one scene"); }
@@ -536,11 +539,18 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     return RT_OK;
 }
 
+// host dry runs compile with the product's defaults; RT_B200_NO_PRUNE=1 (development) shows the stream before box pruning
+static CompileOptions dry_run_options() {
+    CompileOptions o;
+    if (const char* e = std::getenv("RT_B200_NO_PRUNE")) o.prune_boxes = std::atoi(e) == 0;
+    return o;
+}
+
 int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out) {
     if (!desc || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_layout: null argument");
     CompiledScene cs;
     const char* err = nullptr;
-    const int rc = compile_scene(desc, CompileOptions(), &cs, &err);
+    const int rc = compile_scene(desc, dry_run_options(), &cs, &err);
     if (rc < 0) return fail(rc, err ? err : "compile_scene failed");
     std::memset(out, 0, sizeof(*out));
     out->n_words = cs.n_world_words;
@@ -567,6 +577,25 @@ int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out) {
                     (int64_t)cs.perlin_perm.size() + (int64_t)cs.precise.size() * 32;
     for (int k = 0; k < desc->n_images; ++k) bytes += (int64_t)desc->images[k].width * desc->images[k].height * 16;
     out->device_bytes = bytes;
+    return RT_OK;
+}
+
+int rt_scene_ops_export(const rt_scene_desc* desc, float* words, int64_t capacity_words, int64_t* n_total_words,
+                        int32_t* n_world_words, int32_t* media_ops, int32_t* n_media, int32_t* first_class) {
+    if (!desc || !n_total_words) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_ops_export: null argument");
+    CompiledScene cs;
+    const char* err = nullptr;
+    const int rc = compile_scene(desc, dry_run_options(), &cs, &err);
+    if (rc < 0) return fail(rc, err ? err : "compile_scene failed");
+    *n_total_words = (int64_t)cs.ops.size();
+    if (n_world_words) *n_world_words = cs.n_world_words;
+    if (n_media) *n_media = (int32_t)cs.hoisted_media.size();
+    if (media_ops) for (size_t k = 0; k < cs.hoisted_media.size() && k < (size_t)kMaxHoistedMedia; ++k) media_ops[k] = cs.hoisted_media[k];
+    if (first_class) *first_class = (int32_t)cs.first_class;
+    if (words) {
+        if (capacity_words < (int64_t)cs.ops.size()) return fail(RT_ERR_OUT_OF_RANGE, "rt_scene_ops_export: capacity too small");
+        std::memcpy(words, cs.ops.data(), cs.ops.size() * sizeof(F4));
+    }
     return RT_OK;
 }
 

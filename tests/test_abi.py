@@ -96,5 +96,5 @@ def test_cpp_mirror_header_builds_and_runs(rt, tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([exe, "2"], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
-    assert "25 hittables, 15 bvh nodes -> 56 stream words (7 inner, 6 quad, 2 box, 2 instance ops)" in out.stdout
+    assert "25 hittables, 15 bvh nodes -> 46 stream words (2 inner, 6 quad, 2 box, 2 instance ops)" in out.stdout
     assert ("no GPU" in out.stdout) or ("rendered 200x200" in out.stdout)

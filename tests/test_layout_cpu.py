@@ -6,7 +6,13 @@ import pytest
 from conftest import small_scene
 
 
-def test_final_scene_layout(rt):
+@pytest.fixture
+def unpruned(monkeypatch):
+    """The stream as flattened, before the cull boxes that do not pay for themselves are dropped (prune_stream)."""
+    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
+
+
+def test_final_scene_layout(rt, unpruned):
     s, _ = small_scene(rt, 8, rt.synthetic_earth(64, 32))
     L = rt.scene_layout(s)
     assert L["n_box"] == 400                      # 400 Quad::cube lists -> 400 slab primitives (2400 quads in the description)
@@ -19,13 +25,29 @@ def test_final_scene_layout(rt):
     assert L["device_bytes"] < 400_000            # everything but full-size texels fits L1/L2 (earth here is a 64x32 stand-in)
 
 
-def test_other_scenes_layout(rt):
+def test_other_scenes_layout(rt, unpruned):
     L0 = rt.scene_layout(small_scene(rt, 0)[0])
     assert L0["n_precise_spheres"] == 1 and L0["n_box"] == 0 and L0["n_sphere"] == L0["n_inner"] + 1
     L6 = rt.scene_layout(small_scene(rt, 6)[0])
     assert (L6["n_quad"], L6["n_box"], L6["n_xform"], L6["n_inner"]) == (6, 2, 2, 7)
     L7 = rt.scene_layout(small_scene(rt, 7)[0])
     assert (L7["n_quad"], L7["n_box"], L7["n_xform"], L7["n_medium_hoisted"]) == (6, 0, 0, 2)   # boxes only bound media
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_box_pruning_drops_only_cull_boxes(rt, idx, monkeypatch):
+    """prune_stream removes OP_INNER nodes whose expected saving is below their cost (surface-area model); every
+    primitive, instance and medium stays, in the same order; OP_INNER_REF nodes (semantics, not culling) stay."""
+    s, _ = small_scene(rt, idx, rt.synthetic_earth(64, 32) if idx in (2, 8) else None)
+    pruned = rt.scene_layout(s)
+    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
+    full = rt.scene_layout(s)
+    for k in ("n_sphere", "n_quad", "n_box", "n_xform", "n_medium_in_stream", "n_medium_hoisted", "n_bvh", "n_precise_spheres"):
+        assert pruned[k] == full[k], k
+    assert pruned["n_inner"] <= full["n_inner"]
+    assert pruned["n_words"] == full["n_words"] - 2 * (full["n_inner"] - pruned["n_inner"])
+    if idx in (0, 6, 7, 8):
+        assert pruned["n_inner"] < full["n_inner"]
 
 
 def test_degenerate_cube_keeps_its_quads(rt):
@@ -36,7 +58,7 @@ def test_degenerate_cube_keeps_its_quads(rt):
     assert L["n_box"] == 0 and L["n_quad"] == 6
 
 
-def test_quads_that_stick_out_of_their_box_get_reference_nodes(rt):
+def test_quads_that_stick_out_of_their_box_get_reference_nodes(rt, unpruned):
     """Quad::new boxes the diagonal q .. q+u+v only (quad.rs:41-43). For such a quad every BVH node above it, its own
     leaf included, is emitted with the reference's box and per-axis test (OP_INNER_REF) instead of a tight box."""
     def layout(skew):

@@ -1,0 +1,132 @@
+"""The flattening, checked without a GPU: the op stream scene_compile.cpp produces (rt_scene_ops_export) is walked on
+the host by tests/opstream.py - op for op what traverse<>() in rt_kernels.cuh does - and its closest hits must be the
+f64 oracle's: same hit / miss, same primitive (up to exact ties between coplanar faces, where the oracle itself decides
+by rounding noise), same t up to the f32 rounding of the stream's geometry. Covers skip links, visiting order, the
+interval rules, instance folding, hoisted and in-stream media, Quad::cube slab primitives and OP_INNER_REF nodes.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import small_scene
+import opstream
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+from gpu_probe import make_rays  # noqa: E402
+from fuzz_scenes import random_scene  # noqa: E402
+
+T_REL = 2e-5       # stream geometry is f32 (centres, radii, plane offsets, instance sin / cos), the walk itself f64
+
+
+def compare(emu, ref, max_flips=0):
+    flips = int((emu["hit"] != ref["hit"]).sum())
+    assert flips <= max_flips, f"{flips} hit/miss flips"
+    both = (emu["hit"] == 1) & (ref["hit"] == 1)
+    if not both.any():
+        return
+    t_err = np.abs(emu["t"] - ref["t"])[both] / np.maximum(1.0, np.abs(ref["t"][both]))
+    assert t_err.max() <= T_REL, t_err.max()
+    other = emu["prim_id"][both] != ref["prim_id"][both]
+    assert int((other & (t_err > 1e-9)).sum()) == 0            # a different primitive only as an exact tie in t
+    assert int(other.sum()) <= max(2, int(both.sum()) // 200)
+
+
+def random_rays(rt, rng, n, extent=14.0):
+    rays = np.zeros(n, dtype=rt._abi.ray_dtype())
+    rays["origin"] = rng.uniform(-extent, extent, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.5, 2, (n, 1))
+    rays["time"] = rng.random(n)
+    return rays
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_stream_walk_matches_oracle_cli_scenes(rt, ob, earth, idx):
+    s, cam = small_scene(rt, idx, earth)
+    S = opstream.Stream(rt.scene_ops(s))
+    rays = make_rays(cam, s.desc, 1 << 13, seed=7)
+    counts = {}
+    emu = opstream.hit_batch(S, rays, seed=7, counts=counts)
+    compare(emu, ob.hit_batch(s.desc, rays, seed=7), max_flips=1)
+    L = rt.scene_layout(s)
+    assert (counts.get("box", 0) > 0) == (L["n_box"] > 0) and (counts.get("medium", 0) > 0) == (L["n_medium_hoisted"] + L["n_medium_in_stream"] > 0)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_stream_walk_matches_oracle_random_scenes(rt, ob, seed):
+    """Generated scenes (tools/fuzz_scenes.py). Most of their quads stick out of the diagonal box Quad::new gives them
+    (quad.rs:41-43), so which part of them a BVH can see is decided by the reference's own per-axis box test."""
+    s = random_scene(1000 + seed)
+    S = opstream.Stream(rt.scene_ops(s))
+    rays = random_rays(rt, np.random.default_rng(seed), 1 << 14)
+    compare(opstream.hit_batch(S, rays, seed=seed), ob.hit_batch(s.desc, rays, seed=seed), max_flips=1)
+
+
+def test_reference_nodes_decide_what_a_skewed_quad_shows(rt, ob):
+    """One skewed quad in a BVH: the reference culls the part outside its diagonal box (mostly - the per-axis test lets
+    some of it through). The stream must reproduce the oracle exactly; a tight, geometrically complete box would not."""
+    s = rt.Scene(bvh_seed=3)
+    m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))
+    l = rt.HittableList()
+    l.add(s.Quad((-2, -2, 0), (4, 0, 3), (0, 4, -3), m))       # corners q+u and q+v stick out in z
+    l.add(s.Sphere((9, 0, 0), 1.0, m))
+    s.finish(s.BVHNode(l))
+    S = opstream.Stream(rt.scene_ops(s))
+    kinds = S.i[:S.n_world, 3] & 15
+    assert (kinds == opstream.OP_INNER_REF).sum() >= 2          # root and the quad's own leaf box
+    rng = np.random.default_rng(1)
+    n = 1 << 14
+    rays = np.zeros(n, dtype=rt._abi.ray_dtype())
+    rays["origin"] = np.column_stack([np.full(n, -9.0), rng.uniform(-3, 3, n), rng.uniform(-3, 3, n)])      # from the side:
+    rays["direction"] = np.column_stack([np.full(n, 1.0), rng.uniform(-0.1, 0.1, n), rng.uniform(-0.1, 0.1, n)])   # the z slab decides
+    ref = ob.hit_batch(s.desc, rays)
+    compare(opstream.hit_batch(S, rays), ref)
+    # the plain quad (a list world has no boxes, hittable.rs:61-79) is hit by more of these rays than the BVH one
+    s2 = rt.Scene(bvh_seed=3)
+    m2 = s2.Lambertian(s2.SolidColor(0.5, 0.5, 0.5))
+    l2 = rt.HittableList()
+    l2.add(s2.Quad((-2, -2, 0), (4, 0, 3), (0, 4, -3), m2))
+    s2.finish(s2.List(l2))
+    full = ob.hit_batch(s2.desc, rays)
+    assert int(full["hit"].sum()) > int(ref["hit"].sum()) > 0
+    compare(opstream.hit_batch(opstream.Stream(rt.scene_ops(s2)), rays), full)
+
+
+def test_stream_walk_instances_media_and_nesting(rt, ob):
+    """Wrappers in orders the CLI scenes do not use, media with a moving-sphere / rotated-cube / generic boundary,
+    a medium inside an instance (stays in the stream), BVH in BVH, a list world."""
+    rng = np.random.default_rng(8)
+    s = rt.Scene(bvh_seed=5)
+    white = s.Lambertian(s.SolidColor(0.7, 0.7, 0.7))
+    glass = s.Dielectric(1.5)
+    world = rt.HittableList()
+    world.add(s.Translate(s.Sphere((0, 0, 0), 1.0, white), (4, 0, 0)))
+    world.add(s.RotateY(s.cube((-1, -1, -1), (1, 2, 1), white), 30.0))
+    world.add(s.RotateY(s.Translate(s.Quad((0, 0, 0), (2, 0, 0), (0, 2, 0), glass), (0, 3, 1)), -40.0))
+    inner = rt.HittableList()
+    for _ in range(40):
+        c = rng.uniform(-3, 3, 3)
+        inner.add(s.Sphere(c, 0.4, white, target=c + rng.uniform(-0.5, 0.5, 3)))
+    world.add(s.Translate(s.RotateY(s.BVHNode(inner), 75.0), (-8, 0, -2)))
+    nested = rt.HittableList()
+    nested.add(s.BVHNode(inner))
+    nested.add(s.Sphere((0, 8, 0), 2.0, glass))
+    world.add(s.BVHNode(nested))
+    c0 = np.array([8.0, 4.0, 0.0])
+    world.add(s.ConstantMedium(s.Sphere(c0, 2.0, glass, target=c0 + (0, 1, 0)), 0.7, (1, 1, 1)))
+    world.add(s.ConstantMedium(s.Translate(s.RotateY(s.cube((0, 0, 0), (3, 3, 3), white), 20.0), (-4, -6, 0)), 0.9, (0.2, 0.2, 0.2)))
+    two = rt.HittableList()
+    two.add(s.Sphere((0, -9, 6), 1.5, white))
+    two.add(s.cube((-1, -11, 3), (1, -8, 5), white))
+    world.add(s.ConstantMedium(s.BVHNode(two), 1.1, (0.5, 0.5, 0.5)))                                   # generic boundary
+    world.add(s.Translate(s.ConstantMedium(s.Sphere((0, 0, 0), 1.5, glass), 0.8, (1, 1, 1)), (9, -7, -5)))   # medium in an instance
+    s.finish(s.List(world))
+    L = rt.scene_layout(s)
+    assert L["n_medium_in_stream"] == 2 and L["n_medium_hoisted"] == 2
+    S = opstream.Stream(rt.scene_ops(s))
+    rays = random_rays(rt, rng, 1 << 15)
+    ref = ob.hit_batch(s.desc, rays, seed=3)
+    assert len(set(ref["prim_id"][ref["hit"] == 1])) > 30
+    compare(opstream.hit_batch(S, rays, seed=3), ref, max_flips=1)
