@@ -86,6 +86,8 @@ struct CompileOptions {
     bool hoist_media = true;      // false: media stay in the op stream at their BVH position
     bool box_class = false;       // true: OP_BOX lanes vote as CLS_BOX instead of diverging inside the slab class
     bool prune_boxes = true;      // drop cull boxes (OP_INNER) that cost more tests than they save (scene_compile.cpp, prune_stream)
+    // prune_stream's cost of one leaf op relative to one OP_INNER test (what a lane-op of that kind costs the warp)
+    double cost_sphere = 2.5, cost_quad = 1.5, cost_box = 6.0, cost_medium = 6.0, cost_xform = 3.0;
 };
 
 // Returns 0 or a negative rt_status; message in *err.

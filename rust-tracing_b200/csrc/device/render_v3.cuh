@@ -73,6 +73,17 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
     for (int k = 0; k < (COUNT ? (int)K_NUM : 2); ++k) cnt[k] = 0;
 #define CNT(k) do { if (COUNT || (k) < 2) cnt[(COUNT || (k) < 2) ? (k) : 0]++; } while (0)
 #define FETCH_NEXT() do { w0 = __ldg(ops + T.i); w1 = __ldg(ops + T.i + 1); } while (0)
+#define V3_INNER_STEP(HDR) do {                                                                                   \
+        const float ax = (w0.x - T.o.x) * T.inv.x, bx = (w1.x - T.o.x) * T.inv.x;                                 \
+        const float ay = (w0.y - T.o.y) * T.inv.y, by = (w1.y - T.o.y) * T.inv.y;                                 \
+        const float az = (w0.z - T.o.z) * T.inv.z, bz = (w1.z - T.o.z) * T.inv.z;                                 \
+        const bool sx = T.inv.x < 0.0f, sy = T.inv.y < 0.0f, sz = T.inv.z < 0.0f;                                 \
+        const float te = fmaxf(fmaxf(fmaxf(sx ? bx : ax, sy ? by : ay), sz ? bz : az), tmin);                     \
+        const float tx = fminf(fminf(fminf(sx ? ax : bx, sy ? ay : by), sz ? az : bz), T.best.t);                 \
+        const bool hit = te <= tx * 1.0000012f;     /* te >= tmin > 0, so a negative tx can never pass */         \
+        T.i = hit ? T.i + 2 : fbits(w1.w);                                                                        \
+        cls = ((HDR) >> (hit ? 8 : 11)) & 7u;                                                                     \
+    } while (0)
 
     for (;;) {
         unsigned pick;
@@ -111,20 +122,25 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                 if (cls == CLS_SLAB) {
                     const uint32_t hdr = (uint32_t)fbits(w0.w);
                     const uint32_t kind = hdr & 15u;
+                    bool refetch = true;
                     if (COUNT) { cnt[kind == OP_BOX ? K_BOX : K_SLAB]++; if (kind == OP_XFORM_ENTER) cnt[K_XFORM_ENTER]++; }
                     if (kind == OP_INNER) {
                         // AABB::hit (aabb.rs:64-84), tight slab form; see slab_interval() for the NaN / sign rules.
                         // (Folding OP_BOX into this stream was measured: the extra selects on every inner node cost
                         // more than the box/inner divergence they remove, -4% on final_scene, -12% on random_balls.)
-                        const float ax = (w0.x - T.o.x) * T.inv.x, bx = (w1.x - T.o.x) * T.inv.x;
-                        const float ay = (w0.y - T.o.y) * T.inv.y, by = (w1.y - T.o.y) * T.inv.y;
-                        const float az = (w0.z - T.o.z) * T.inv.z, bz = (w1.z - T.o.z) * T.inv.z;
-                        const bool sx = T.inv.x < 0.0f, sy = T.inv.y < 0.0f, sz = T.inv.z < 0.0f;
-                        const float te = fmaxf(fmaxf(fmaxf(sx ? bx : ax, sy ? by : ay), sz ? bz : az), tmin);
-                        const float tx = fminf(fminf(fminf(sx ? ax : bx, sy ? ay : by), sz ? az : bz), T.best.t);
-                        const bool hit = te <= tx * 1.0000012f;     // te >= tmin > 0, so a negative tx can never pass
-                        T.i = hit ? T.i + 2 : fbits(w1.w);
-                        cls = (hdr >> (hit ? 8 : 11)) & 7u;
+                        V3_INNER_STEP(hdr);
+#ifdef RT_OPT_SLAB_DOUBLE
+                        // a second inner node in the same repetition for the lanes that are at one again: saves the
+                        // loop control and the class test between the two
+                        FETCH_NEXT();
+                        const uint32_t hdr2 = (uint32_t)fbits(w0.w);
+                        if (cls == CLS_SLAB && (hdr2 & 15u) == OP_INNER) {
+                            if (COUNT) cnt[K_SLAB]++;
+                            V3_INNER_STEP(hdr2);
+                        } else {
+                            refetch = false;
+                        }
+#endif
                     } else if (kind == OP_XFORM_EXIT) {
                         T.o = f3(COLD(0), COLD(1), COLD(2));
                         T.d = f3(COLD(3), COLD(4), COLD(5));
@@ -137,7 +153,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                         cls = op_slab_class(S, T, w0, w1, tmin, origin);   // BOX, XFORM_ENTER (the world ray stays in COLD)
                         if (COUNT && T.best.t != tb) cnt[K_BOX_HIT]++;
                     }
-                    FETCH_NEXT();
+                    if (refetch) FETCH_NEXT();
                 }
                 if (__popc(__ballot_sync(0xffffffffu, cls == CLS_SLAB)) < (unsigned)prm.slab_exit) break;   // too few left: vote again
             }
@@ -314,6 +330,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
     }
 #undef CNT
 #undef FETCH_NEXT
+#undef V3_INNER_STEP
 #undef COLD
 #undef COLD_U
     for (int k = 0; k < (COUNT ? (int)K_NUM : 2); ++k) {   // one atomic per warp and counter

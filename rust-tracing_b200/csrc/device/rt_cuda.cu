@@ -470,17 +470,27 @@ static int upload_vec(rt_scene* s, const void* src, size_t bytes, void** dst) {
     return RT_OK;
 }
 
+// host dry runs compile with the product's defaults; RT_B200_NO_PRUNE=1 (development) shows the stream before box pruning
+static CompileOptions dry_run_options() {
+    CompileOptions o;
+    if (const char* e = std::getenv("RT_B200_NO_PRUNE")) o.prune_boxes = std::atoi(e) == 0;
+    if (const char* e = std::getenv("RT_B200_COST_SPHERE")) o.cost_sphere = std::atof(e);
+    if (const char* e = std::getenv("RT_B200_COST_QUAD")) o.cost_quad = std::atof(e);
+    if (const char* e = std::getenv("RT_B200_COST_BOX")) o.cost_box = std::atof(e);
+    return o;
+}
+
 int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     if (!c || !desc || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: null argument");
     CU(cudaSetDevice(c->device));
     rt_scene* s = new rt_scene;
     s->ctx = c;
     const char* err = nullptr;
-    CompileOptions copt;
+    CompileOptions copt = dry_run_options();
     copt.box_primitives = c->box_primitives;
     copt.hoist_media = c->hoist_media;
     copt.box_class = c->box_class && c->variant == 3;
-    copt.prune_boxes = c->prune_boxes;
+    copt.prune_boxes = c->prune_boxes && copt.prune_boxes;
     int rc = compile_scene(desc, copt, &s->compiled, &err);
     if (rc < 0) { delete s; return fail(rc, err ? err : "compile_scene failed"); }
     if (s->compiled.n_perlin > kMaxPerlinShared) { delete s; return fail(RT_ERR_UNSUPPORTED, "more than 4 NoiseTexture tables in one scene"); }
@@ -537,13 +547,6 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     s->dev.images = static_cast<const DevImage*>(p);
     *out = s;
     return RT_OK;
-}
-
-// host dry runs compile with the product's defaults; RT_B200_NO_PRUNE=1 (development) shows the stream before box pruning
-static CompileOptions dry_run_options() {
-    CompileOptions o;
-    if (const char* e = std::getenv("RT_B200_NO_PRUNE")) o.prune_boxes = std::atoi(e) == 0;
-    return o;
 }
 
 int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out) {

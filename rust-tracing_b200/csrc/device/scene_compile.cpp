@@ -424,7 +424,8 @@ struct Pruner {
     const std::vector<F4>& in;
     std::vector<F4> out;
     std::unordered_map<uint64_t, std::vector<std::pair<double, double>>> memo;   // at -> [(ancestor area, cost)]
-    explicit Pruner(const std::vector<F4>& ops) : in(ops) {}
+    CompileOptions opt;
+    Pruner(const std::vector<F4>& ops, const CompileOptions& o) : in(ops), opt(o) {}
 
     static uint32_t hdr_of(const F4& w) { uint32_t u; std::memcpy(&u, &w.w, 4); return u; }
     static int32_t int_of(float f) { int32_t v; std::memcpy(&v, &f, 4); return v; }
@@ -489,10 +490,10 @@ struct Pruner {
     // relative costs of one op for a lane (instructions of the op's body in the render kernel, OP_INNER = 1)
     double cost(const IrNode& n, double ancestor) {
         switch (n.kind) {
-            case OP_SPHERE: return 1.4;
-            case OP_QUAD: return 1.5;
-            case OP_BOX: return 1.6;
-            case OP_MEDIUM: return 6.0;
+            case OP_SPHERE: return opt.cost_sphere;
+            case OP_QUAD: return opt.cost_quad;
+            case OP_BOX: return opt.cost_box;
+            case OP_MEDIUM: return opt.cost_medium;
             default: break;
         }
         auto& slot = memo[(uint64_t)n.at];
@@ -503,7 +504,7 @@ struct Pruner {
             const double k = 1.0 + p * cost_list(n.ch, n.area), dsv = cost_list(n.ch, ancestor);
             c = k <= dsv ? k : dsv;
         } else if (n.kind == OP_XFORM_ENTER) {
-            c = 3.0 + p * (cost_list(n.ch, n.area) + 0.5);
+            c = opt.cost_xform + p * (cost_list(n.ch, n.area) + 0.5);
         } else {   // OP_INNER_REF, frozen OP_INNER
             c = 1.0 + p * cost_list(n.ch, n.area);
         }
@@ -551,9 +552,9 @@ struct Pruner {
     }
 };
 
-void prune_stream(std::vector<F4>* ops) {
+void prune_stream(std::vector<F4>* ops, const CompileOptions& opt) {
     if (ops->empty()) return;
-    Pruner p(*ops);
+    Pruner p(*ops, opt);
     const std::vector<IrNode> tree = p.parse(0, (int)ops->size(), false);
     p.emit_list(tree, std::numeric_limits<double>::infinity());
     ops->swap(p.out);
@@ -627,7 +628,7 @@ int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, Compiled
         out->ops.push_back(F4{-inf, -inf, -inf, int_to_float_bits(2)});
     }
     if (c.status) { msg = c.err; if (err) *err = msg.c_str(); return c.status; }
-    if (opt.prune_boxes) prune_stream(&out->ops);
+    if (opt.prune_boxes) prune_stream(&out->ops, opt);
 
     // successor classes into the header bits (dev_scene.h)
     {
