@@ -11,7 +11,8 @@ REPS = [('r1_a_v1_whole_segment_loop', 'prof_r1_a.ncu-rep', 'v1: every lane trac
         ('r1_c4_v3_128regs', 'prof_r1_c4.ncu-rep', 'v3 @ 4 blocks/SM (cold state in shared memory), before the code-size work'),
         ('r1_c6_v3_80regs', 'prof_r1_c6.ncu-rep', 'v3 @ 6 blocks/SM, before the code-size work (I-cache thrash)'),
         ('r1_d_v3_small_code', 'prof_r1_d.ncu-rep', 'v3 @ 5 blocks/SM after shrinking the instruction footprint'),
-        ('r1_e_v3_default', 'prof_r1_e.ncu-rep', 'v3 @ 6 blocks/SM, fast div/sqrt build (current default)')]
+        ('r1_e_v3_default', 'prof_r1_e.ncu-rep', 'v3 @ 6 blocks/SM, fast div/sqrt build'),
+        ('r1_f_v3_pruned_stream', 'prof_r1_f.ncu-rep', 'v3 @ 6 blocks/SM on the pruned op stream (prune_stream; current default)')]
 KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
@@ -73,7 +74,7 @@ def main():
              'The path is not FP32-throughput bound; it is bound by SIMT divergence and per-op overhead.'.format(hw, 100 * hw / 37888))
     L.append('* Lanes per executed instruction {} of 32: lanes of minority classes (sphere, shade) wait for the vote while the slab class runs.'.format(
         d['smsp__thread_inst_executed_per_inst_executed.ratio']))
-    L.append('* {:.0f} warp-instructions per path; about 60% are slab-class repetitions (~75 instructions per repetition including loop control, ~12 active lanes).'.format(
+    L.append('* {:.0f} warp-instructions per path; about half are slab-class repetitions (57 instructions per repetition including loop control and the next-op fetch, ~10-11 active lanes; SASS view of r1_e and of the wavefront extend kernel).'.format(
         g(d, 'smsp__inst_executed.sum') / PATHS))
     L.append('* Issue slots {:.1f}% busy; per issued instruction {:.2f} `wait` (fixed-latency dependency), {:.2f} `not_selected`, {:.2f} `no_instruction`, {:.2f} `branch_resolving`, {:.2f} `long_scoreboard`.'.format(
         g(d, 'smsp__issue_active.avg.pct_of_peak_sustained_active'), g(d, 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio'),
