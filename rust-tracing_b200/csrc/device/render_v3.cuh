@@ -32,7 +32,7 @@ inline size_t v3_smem_bytes(int n_perlin) {
     return (size_t)np * (256 + 48) * sizeof(float4) + (size_t)kColdFields * kBlockThreads * sizeof(float);
 }
 
-template <bool COUNT, int MIN_BLOCKS>
+template <bool COUNT, int MIN_BLOCKS, bool FOLD>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(const RenderParams prm) {
     // dynamic shared memory: [n_perlin x 256 float4 gradients][n_perlin x 768 B permutations][cold state]
     const int np = min(prm.scene.n_perlin, kMaxPerlinShared);
@@ -124,23 +124,51 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                     const uint32_t kind = hdr & 15u;
                     bool refetch = true;
                     if (COUNT) { cnt[kind == OP_BOX ? K_BOX : K_SLAB]++; if (kind == OP_XFORM_ENTER) cnt[K_XFORM_ENTER]++; }
-                    if (kind == OP_INNER) {
-                        // AABB::hit (aabb.rs:64-84), tight slab form; see slab_interval() for the NaN / sign rules.
-                        // (Folding OP_BOX into this stream was measured: the extra selects on every inner node cost
-                        // more than the box/inner divergence they remove, -4% on final_scene, -12% on random_balls.)
-                        V3_INNER_STEP(hdr);
-#ifdef RT_OPT_SLAB_DOUBLE
-                        // a second inner node in the same repetition for the lanes that are at one again: saves the
-                        // loop control and the class test between the two
-                        FETCH_NEXT();
-                        const uint32_t hdr2 = (uint32_t)fbits(w0.w);
-                        if (cls == CLS_SLAB && (hdr2 & 15u) == OP_INNER) {
-                            if (COUNT) cnt[K_SLAB]++;
-                            V3_INNER_STEP(hdr2);
+                    // FOLD: OP_BOX shares the slab arithmetic of OP_INNER (same lanes, same instructions) and differs only
+                    // in what it does with the unclamped entry / exit parameters. It costs every inner node ~5 more
+                    // instructions and saves the divergent OP_BOX path, which ran at 2.3 lanes and was 15% of all issued
+                    // instructions on final_scene once the stream was pruned: +3.6% there, -2..-3.5% on scenes with few or
+                    // no cubes (profiles/r1_ab23_fold_box.log), so the host picks it per scene (launch_render).
+                    const bool box_fast = FOLD && kind == OP_BOX && !((origin >> 3) == T.i && origin >= 0);
+                    if (kind == OP_INNER || box_fast) {
+                        if (FOLD) {
+                            const float ax = (w0.x - T.o.x) * T.inv.x, bx = (w1.x - T.o.x) * T.inv.x;
+                            const float ay = (w0.y - T.o.y) * T.inv.y, by = (w1.y - T.o.y) * T.inv.y;
+                            const float az = (w0.z - T.o.z) * T.inv.z, bz = (w1.z - T.o.z) * T.inv.z;
+                            const bool sx = T.inv.x < 0.0f, sy = T.inv.y < 0.0f, sz = T.inv.z < 0.0f;
+                            const float te_raw = fmaxf(fmaxf(sx ? bx : ax, sy ? by : ay), sz ? bz : az);
+                            const float tx_raw = fminf(fminf(sx ? ax : bx, sy ? ay : by), sz ? az : bz);
+                            if (box_fast) {      // Quad::cube as one slab primitive, see op_box()
+                                float t = te_raw;
+                                if (!(tmin <= t && t <= T.best.t)) t = tx_raw;
+                                if (te_raw <= tx_raw && tmin <= t && t <= T.best.t) {
+                                    if (COUNT) cnt[K_BOX_HIT]++;
+                                    T.best.t = t; T.best.op = T.i; T.best.xf = T.cur_xf;
+                                }
+                                T.i += 3;
+                                cls = (hdr >> 8) & 7u;
+                            } else {             // AABB::hit (aabb.rs:64-84), tight slab form
+                                const float te = fmaxf(te_raw, tmin), tx = fminf(tx_raw, T.best.t);
+                                const bool hit = te <= tx * 1.0000012f;
+                                T.i = hit ? T.i + 2 : fbits(w1.w);
+                                cls = (hdr >> (hit ? 8 : 11)) & 7u;
+                            }
                         } else {
-                            refetch = false;
-                        }
+                            // AABB::hit (aabb.rs:64-84), tight slab form; see slab_interval() for the NaN / sign rules
+                            V3_INNER_STEP(hdr);
+#ifdef RT_OPT_SLAB_DOUBLE
+                            // a second inner node in the same repetition for the lanes that are at one again: saves the
+                            // loop control and the class test between the two (measured: -7% final_scene, +2..5% random_balls)
+                            FETCH_NEXT();
+                            const uint32_t hdr2 = (uint32_t)fbits(w0.w);
+                            if (cls == CLS_SLAB && (hdr2 & 15u) == OP_INNER) {
+                                if (COUNT) cnt[K_SLAB]++;
+                                V3_INNER_STEP(hdr2);
+                            } else {
+                                refetch = false;
+                            }
 #endif
+                        }
                     } else if (kind == OP_XFORM_EXIT) {
                         T.o = f3(COLD(0), COLD(1), COLD(2));
                         T.d = f3(COLD(3), COLD(4), COLD(5));

@@ -300,18 +300,26 @@ DevCamera make_dev_camera(const rt_camera_desc& c) {
 }  // namespace
 
 typedef void (*render_fn)(const RenderParams);
-static render_fn v3_kernel(bool counting, int min_blocks) {
-    if (counting) return render_kernel_v3<true, 1>;
+static render_fn v3_kernel(bool counting, int min_blocks, bool fold) {
+    if (counting) return render_kernel_v3<true, 1, false>;
+    if (fold) {
+        switch (min_blocks) {
+            case 5: return render_kernel_v3<false, 5, true>;
+            case 4: return render_kernel_v3<false, 4, true>;
+            default: return render_kernel_v3<false, 6, true>;
+        }
+    }
     switch (min_blocks) {
-        case 8: return render_kernel_v3<false, 8>;
-        case 7: return render_kernel_v3<false, 7>;
-        case 3: return render_kernel_v3<false, 3>;
-        case 2: return render_kernel_v3<false, 2>;
-        case 6: return render_kernel_v3<false, 6>;
-        case 5: return render_kernel_v3<false, 5>;
-        default: return render_kernel_v3<false, 4>;
+        case 8: return render_kernel_v3<false, 8, false>;
+        case 7: return render_kernel_v3<false, 7, false>;
+        case 3: return render_kernel_v3<false, 3, false>;
+        case 2: return render_kernel_v3<false, 2, false>;
+        case 6: return render_kernel_v3<false, 6, false>;
+        case 5: return render_kernel_v3<false, 5, false>;
+        default: return render_kernel_v3<false, 4, false>;
     }
 }
+constexpr int kFoldBoxMin = 64;   // scenes with at least this many cube primitives run the FOLD form of the kernel (render_v3.cuh)
 
 typedef void (*wf_extend_fn)(const WfParams);
 typedef void (*wf_shade_fn)(const WfParams, const int);
@@ -363,6 +371,7 @@ struct rt_context {
     int slab_fast = 14, slab_reps = 8, sphere_reps = 2;
     int slab_exit = 1, sphere_min = 33, box_min = 33, quad_min = 33;
     bool box_class = false;
+    int fold_box = -1;           // -1: per scene (kFoldBoxMin); 0 / 1 forced (RT_B200_FOLD_BOX, A/B runs)
     bool prune_boxes = true;
     bool box_primitives = true;
     unsigned int* d_counter = nullptr;
@@ -375,6 +384,7 @@ struct rt_context {
 
 struct rt_scene {
     rt_context* ctx = nullptr;
+    int n_box = 0;               // OP_BOX primitives in the world program
     DevScene dev{};
     std::vector<void*> allocations;
     CompiledScene compiled;
@@ -417,12 +427,15 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* e = std::getenv("RT_B200_QUAD_MIN")) c->quad_min = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RT_B200_BOX_CLASS")) c->box_class = std::atoi(e) != 0;
     if (const char* e = std::getenv("RT_B200_NO_PRUNE")) c->prune_boxes = std::atoi(e) == 0;
+    if (const char* e = std::getenv("RT_B200_FOLD_BOX")) c->fold_box = std::atoi(e) != 0 ? 1 : 0;
     if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
     if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 2 ? v : 4; }
     CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
     for (int mb : {2, 3, 4, 5, 6, 7, 8})
-        CU(cudaFuncSetAttribute(v3_kernel(false, mb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
-    CU(cudaFuncSetAttribute(v3_kernel(true, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
+        CU(cudaFuncSetAttribute(v3_kernel(false, mb, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
+    for (int mb : {4, 5, 6})
+        CU(cudaFuncSetAttribute(v3_kernel(false, mb, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
+    CU(cudaFuncSetAttribute(v3_kernel(true, 1, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
     CU(cudaMalloc(&c->d_path_counter, sizeof(unsigned long long)));
     CU(cudaMalloc(&c->d_slot_cursor, sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_live, 2 * kWfBatch * sizeof(unsigned int)));
@@ -431,7 +444,7 @@ int rt_context_create(int device_id, rt_context** out) {
     CU(cudaEventCreateWithFlags(&c->wf_event[1], cudaEventDisableTiming));
     int bps = 0;
     if (c->variant == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_kernel, kBlockThreads, perlin_smem_bytes()));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v3_kernel(false, c->min_blocks), kBlockThreads, v3_smem_bytes(1)));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v3_kernel(false, c->min_blocks, false), kBlockThreads, v3_smem_bytes(1)));
     c->blocks_per_sm = bps > 0 ? bps : 1;
     CU(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_stats, K_NUM * sizeof(unsigned long long)));
@@ -508,6 +521,14 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     UP(cs.precise, precise, const double4*)
 #undef UP
     s->dev.n_words = cs.n_world_words;
+    for (int i = 0; i < cs.n_world_words; ++i) {   // words of other ops can alias a header only by accident of their bits:
+        uint32_t hdr;                               // walk op by op
+        std::memcpy(&hdr, &cs.ops[i].w, 4);
+        const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
+        if (kind == OP_BOX) s->n_box++;
+        i += (kind == OP_QUAD || kind == OP_XFORM_ENTER) ? 3 : kind == OP_BOX ? 2 : kind == OP_SPHERE ? ((flags & FLAG_MOVING) ? 2 : 1)
+             : kind == OP_MEDIUM ? ((int)flags == MEDIUM_BOUNDARY_XBOX ? 4 : 2) : 1;
+    }
     s->dev.n_media = (int)cs.hoisted_media.size();
     for (int k = 0; k < s->dev.n_media; ++k) s->dev.media_op[k] = cs.hoisted_media[k];
     s->dev.n_perlin = cs.n_perlin;
@@ -769,7 +790,8 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     int grid = c->sm_count * c->blocks_per_sm;
     if (counting || c->variant == 3) {
         const size_t smem = v3_smem_bytes(s->dev.n_perlin);
-        render_fn fn = v3_kernel(counting, c->min_blocks);
+        const bool fold = c->fold_box < 0 ? s->n_box >= kFoldBoxMin : c->fold_box != 0;
+        render_fn fn = v3_kernel(counting, c->min_blocks, fold);
         int bps = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, kBlockThreads, smem));
         grid = c->sm_count * (bps > 0 ? bps : 1);

@@ -1,7 +1,8 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-for k in 1 2; do
-  echo "== default (pruned)"; timeout 100 python tools/ncu_target.py --spp 1000 --reps 3 | grep rep
-  echo "== RT_B200_NO_PRUNE=1"; RT_B200_NO_PRUNE=1 timeout 100 python tools/ncu_target.py --spp 1000 --reps 3 | grep rep
-done
+LF=$GRAFT_REPO_ROOT/rust-tracing_b200/csrc/librt_b200_fold.so
+RT_B200_LIB=$LF timeout 300 python -m pytest tests/test_gpu_render.py tests/test_gpu_wavefront.py -x -q -m gpu 2>&1 | tail -3
+V='[{},{"RT_B200_LIB":"'$LF'"},{},{"RT_B200_LIB":"'$LF'"}]'
+timeout 400 python tools/ab.py "$V" 8,6,0,7 256 > gpurun_out/ab23.log 2>&1
+sed "s#$GRAFT_REPO_ROOT/rust-tracing_b200/csrc/##" gpurun_out/ab23.log
