@@ -12,7 +12,8 @@ REPS = [('r1_a_v1_whole_segment_loop', 'prof_r1_a.ncu-rep', 'v1: every lane trac
         ('r1_c6_v3_80regs', 'prof_r1_c6.ncu-rep', 'v3 @ 6 blocks/SM, before the code-size work (I-cache thrash)'),
         ('r1_d_v3_small_code', 'prof_r1_d.ncu-rep', 'v3 @ 5 blocks/SM after shrinking the instruction footprint'),
         ('r1_e_v3_default', 'prof_r1_e.ncu-rep', 'v3 @ 6 blocks/SM, fast div/sqrt build'),
-        ('r1_f_v3_pruned_stream', 'prof_r1_f.ncu-rep', 'v3 @ 6 blocks/SM on the pruned op stream (prune_stream; current default)')]
+        ('r1_f_v3_pruned_stream', 'prof_r1_f.ncu-rep', 'v3 @ 6 blocks/SM on the pruned op stream (prune_stream)'),
+        ('r1_g_v3_fold_box', 'prof_r1_g.ncu-rep', 'v3 FOLD form @ 6 blocks/SM on the pruned stream (current default for final_scene)')]
 KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
