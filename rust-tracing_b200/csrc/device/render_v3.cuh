@@ -169,16 +169,12 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
                             }
 #endif
                         }
-                    } else if (kind == OP_XFORM_EXIT) {
-                        T.o = f3(COLD(0), COLD(1), COLD(2));
-                        T.d = f3(COLD(3), COLD(4), COLD(5));
-                        T.inv = safe_inv(T.d);
-                        T.cur_xf = -1;
-                        T.i += 2;
-                        cls = (hdr >> 8) & 7u;
                     } else {
-                        const float tb = T.best.t;
-                        cls = op_slab_class(S, T, w0, w1, tmin, origin);   // BOX, XFORM_ENTER (the world ray stays in COLD)
+                        const float tb = T.best.t;   // BOX, XFORM_ENTER / EXIT, INNER_REF (the world ray stays in COLD)
+                        cls = op_slab_class(S, T, w0, w1, tmin, origin, [&](float3& wo, float3& wd) {
+                            wo = f3(COLD(0), COLD(1), COLD(2));
+                            wd = f3(COLD(3), COLD(4), COLD(5));
+                        });
                         if (COUNT && T.best.t != tb) cnt[K_BOX_HIT]++;
                     }
                     if (refetch) FETCH_NEXT();
@@ -189,7 +185,10 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) render_kernel_v3(co
             if (cls == CLS_BOX) {        // OP_BOX as its own class (CompileOptions::box_class)
                 if (COUNT) cnt[K_BOX]++;
                 const float tb = T.best.t;
-                cls = op_slab_class(S, T, w0, w1, tmin, origin);
+                cls = op_slab_class(S, T, w0, w1, tmin, origin, [&](float3& wo, float3& wd) {
+                    wo = f3(COLD(0), COLD(1), COLD(2));
+                    wd = f3(COLD(3), COLD(4), COLD(5));
+                });
                 if (COUNT && T.best.t != tb) cnt[K_BOX_HIT]++;
                 FETCH_NEXT();
             }

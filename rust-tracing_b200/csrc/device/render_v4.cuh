@@ -270,15 +270,11 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS) wf_extend_kernel(co
                         const bool hit = te <= tx * 1.0000012f;     // te >= tmin > 0, so a negative tx can never pass
                         T.i = hit ? T.i + 2 : fbits(w1.w);
                         cls = (hdr >> (hit ? 8 : 11)) & 7u;
-                    } else if (kind == OP_XFORM_EXIT) {
-                        T.o = f3(__ldg(pool.ray0 + slot));
-                        T.d = f3(__ldg(pool.ray1 + slot));
-                        T.inv = safe_inv(T.d);
-                        T.cur_xf = -1;
-                        T.i += 2;
-                        cls = (hdr >> 8) & 7u;
-                    } else {
-                        cls = op_slab_class(S, T, w0, w1, tmin, origin);   // BOX, XFORM_ENTER
+                    } else {     // BOX, XFORM_ENTER / EXIT, INNER_REF (the world ray stays in the pool)
+                        cls = op_slab_class(S, T, w0, w1, tmin, origin, [&](float3& wo, float3& wd) {
+                            wo = f3(__ldg(pool.ray0 + slot));
+                            wd = f3(__ldg(pool.ray1 + slot));
+                        });
                     }
                     FETCH_NEXT();
                 }

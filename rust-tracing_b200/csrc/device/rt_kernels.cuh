@@ -106,7 +106,7 @@ struct Best {
 // Per-lane traversal cursor over the threaded op stream.
 struct Trav {
     float3 o, d, inv;   // current (possibly instance-local) ray and its reciprocal direction
-    float3 so, sd;      // outer ray while inside an instance
+    float3 so, sd;      // the world ray: every OP_XFORM_ENTER holds the composed world -> local transform, nested or not
     int cur_xf;         // word index of the active OP_XFORM_ENTER, -1 = none
     int i;              // word index of the next op
     Best best;
@@ -155,20 +155,27 @@ __device__ __forceinline__ bool aabb_hit_reference(float4 w0, float4 w1, float3 
     return !(mx || my || mz);
 }
 
-// local = R(x - a) + b with R = rotate-y as in hittable.rs:164-168
+// local = R(x - a) + b with R = rotate-y as in hittable.rs:164-168.
+// Written with explicit round-to-nearest intrinsics, which the compiler never contracts or re-associates: the traversal
+// (entering an instance) and finalize_hit() (recomputing the local ray of the winner) must produce the SAME bits, because
+// a cube's face is recognised by t == plane parameter exactly. With plain operators the two inline sites could get
+// different FMA contractions: a 1-ulp difference then mis-identifies the face, the self-intersection guard of the next
+// segment looks at the wrong plane, and the path re-hits its own surface until max_depth (seen once the instance code
+// was restructured: 8 of 360 000 Cornell paths trapped; the wavefront kernel, compiled separately, was unaffected).
 __device__ __forceinline__ float3 xform_point(float3 x, float4 w2, float4 w3) {
-    const float3 q = x - f3(w2);
+    const float qx = __fsub_rn(x.x, w2.x), qy = __fsub_rn(x.y, w2.y), qz = __fsub_rn(x.z, w2.z);
     const float s = w2.w, c = w3.w;
-    return f3(c * q.x - s * q.z + w3.x, q.y + w3.y, s * q.x + c * q.z + w3.z);
+    return f3(__fadd_rn(__fmaf_rn(c, qx, -__fmul_rn(s, qz)), w3.x), __fadd_rn(qy, w3.y),
+              __fadd_rn(__fmaf_rn(s, qx, __fmul_rn(c, qz)), w3.z));
 }
 __device__ __forceinline__ float3 xform_dir(float3 v, float4 w2, float4 w3) {
     const float s = w2.w, c = w3.w;
-    return f3(c * v.x - s * v.z, v.y, s * v.x + c * v.z);
+    return f3(__fmaf_rn(c, v.x, -__fmul_rn(s, v.z)), v.y, __fmaf_rn(s, v.x, __fmul_rn(c, v.z)));
 }
 // inverse rotation (hittable.rs:173-179)
 __device__ __forceinline__ float3 xform_dir_back(float3 v, float4 w2, float4 w3) {
     const float s = w2.w, c = w3.w;
-    return f3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z);
+    return f3(__fmaf_rn(c, v.x, __fmul_rn(s, v.z)), v.y, __fmaf_rn(-s, v.x, __fmul_rn(c, v.z)));
 }
 
 // Sphere::hit roots (sphere.rs:59-83): false on a negative discriminant, else near/far roots.
@@ -293,12 +300,14 @@ __device__ __forceinline__ void op_box(Trav& T, float4 w0, float4 w1, float tmin
     T.i += 3;
 }
 
+// Translate::hit / RotateY::hit (hittable.rs:96-111,159-193). The box is tested with the current ray (the space the
+// instance sits in); the transform stored in the op is the composition of all enclosing instances, applied to the
+// WORLD ray, so an instance nested in another instance's subtree needs no stack of saved rays.
 __device__ __forceinline__ void op_xform_enter(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin) {
     if (slab(w0, w1, T.o, T.inv, tmin, T.best.t)) {
         const float4 w2 = __ldg(S.ops + T.i + 2), w3 = __ldg(S.ops + T.i + 3);
-        T.so = T.o; T.sd = T.d;
-        T.o = xform_point(T.o, w2, w3);     // hittable.rs:98,164-168
-        T.d = xform_dir(T.d, w2, w3);
+        T.o = xform_point(T.so, w2, w3);     // hittable.rs:98,164-168
+        T.d = xform_dir(T.sd, w2, w3);
         T.inv = safe_inv(T.d);
         T.cur_xf = T.i;
         T.i += 4;
@@ -307,20 +316,38 @@ __device__ __forceinline__ void op_xform_enter(const DevScene& S, Trav& T, float
     }
 }
 
-__device__ __forceinline__ void op_xform_exit(Trav& T) {
-    T.o = T.so; T.d = T.sd;
+// Back in the enclosing space: the world ray, or the world ray through the parent instance named by the exit op.
+__device__ __forceinline__ void xform_restore(const DevScene& S, Trav& T, float3 wo, float3 wd, int parent) {
+    T.o = wo; T.d = wd;
+    if (parent >= 0) {
+        const float4 p2 = __ldg(S.ops + parent + 2), p3 = __ldg(S.ops + parent + 3);
+        T.o = xform_point(wo, p2, p3);
+        T.d = xform_dir(wd, p2, p3);
+    }
     T.inv = safe_inv(T.d);
-    T.cur_xf = -1;
+    T.cur_xf = parent;
+}
+__device__ __forceinline__ void op_xform_exit(const DevScene& S, Trav& T, float4 w0) {
+    xform_restore(S, T, T.so, T.sd, fbits(w0.x));
     T.i += 2;
 }
 
 // INNER / BOX / XFORM_ENTER / XFORM_EXIT in one body that shares the slab arithmetic (the render kernel's
 // "slab class"). Returns the class of the lane's next op, read from the header's successor bits.
-__device__ __forceinline__ uint32_t op_slab_class(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin, int origin) {
+// `world(o, d)` fetches the world ray (the render kernels keep it out of registers); it is called only where an
+// instance is entered from inside another one or left.
+template <class WorldRay>
+__device__ __forceinline__ uint32_t op_slab_class(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin, int origin, WorldRay world) {
     const uint32_t hdr = (uint32_t)fbits(w0.w);
     const uint32_t kind = hdr & 15u;
     const uint32_t ft = (hdr >> 8) & 7u, sk = (hdr >> 11) & 7u;
-    if (kind == OP_XFORM_EXIT) { op_xform_exit(T); return ft; }
+    if (kind == OP_XFORM_EXIT) {
+        float3 wo, wd;
+        world(wo, wd);
+        xform_restore(S, T, wo, wd, fbits(w0.x));
+        T.i += 2;
+        return ft;
+    }
     if (kind == OP_INNER_REF) {
         const bool pass = aabb_hit_reference(w0, w1, T.o, T.inv, tmin, T.best.t);
         T.i = pass ? T.i + 2 : fbits(w1.w);
@@ -344,9 +371,10 @@ __device__ __forceinline__ uint32_t op_slab_class(const DevScene& S, Trav& T, fl
     if (!hit) { T.i = fbits(w1.w); return sk; }
     if (kind == OP_INNER) { T.i += 2; return ft; }
     const float4 w2 = __ldg(S.ops + T.i + 2), w3 = __ldg(S.ops + T.i + 3);   // OP_XFORM_ENTER
-    T.so = T.o; T.sd = T.d;
-    T.o = xform_point(T.o, w2, w3);
-    T.d = xform_dir(T.d, w2, w3);
+    float3 wo = T.o, wd = T.d;
+    if (T.cur_xf >= 0) world(wo, wd);      // nested: the op holds the composed world -> local transform
+    T.o = xform_point(wo, w2, w3);
+    T.d = xform_dir(wd, w2, w3);
     T.inv = safe_inv(T.d);
     T.cur_xf = T.i;
     T.i += 4;
@@ -444,7 +472,7 @@ __device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, 
         else if (kind == OP_BOX) op_box(T, w0, w1, tmin, origin);
         else if (kind == OP_QUAD) op_quad(S, T, w0, w1, tmin, origin);
         else if (kind == OP_XFORM_ENTER) op_xform_enter(S, T, w0, w1, tmin);
-        else if (kind == OP_XFORM_EXIT) op_xform_exit(T);
+        else if (kind == OP_XFORM_EXIT) op_xform_exit(S, T, w0);
         else if (WORLD) op_medium(S, T, w0, w1, ray.time, tmin, key, seg);
         else T.i = end;   // a medium inside a boundary program is rejected at upload
     }

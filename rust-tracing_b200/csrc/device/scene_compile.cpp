@@ -59,7 +59,25 @@ struct Compiler {
     CompileOptions opt;
     std::string err;
     int status = 0;
-    bool in_xform = false;
+    // Enclosing instances, innermost last: word index of the OP_XFORM_ENTER and its COMPOSED world -> local transform
+    // (local = R(x - a) + b). An instance nested in another instance's subtree is emitted with the composition, so the
+    // device always transforms the world ray and needs no stack of saved rays; the matching OP_XFORM_EXIT names its parent.
+    struct XfParams { double a[3], b[3], s, c; };
+    std::vector<std::pair<int, XfParams>> xf_stack;
+    bool boundary_in_xform = false;      // emitting the boundary program of a medium that itself sits inside an instance
+    bool in_xform() const { return !xf_stack.empty(); }
+    static XfParams compose(const XfParams& P, const XfParams& C) {
+        // lp = Rp(x - ap) + bp ; lc = Rc(lp - ac) + bc  =>  lc = (Rc Rp)(x - ap) + Rc(bp - ac) + bc
+        XfParams X;
+        for (int k = 0; k < 3; ++k) X.a[k] = P.a[k];
+        X.s = C.s * P.c + C.c * P.s;
+        X.c = C.c * P.c - C.s * P.s;
+        const double q[3] = {P.b[0] - C.a[0], P.b[1] - C.a[1], P.b[2] - C.a[2]};
+        X.b[0] = C.c * q[0] - C.s * q[2] + C.b[0];
+        X.b[1] = q[1] + C.b[1];
+        X.b[2] = C.s * q[0] + C.c * q[2] + C.b[2];
+        return X;
+    }
     std::vector<Box> tight_hittable;  // memo, by hittable id
     std::vector<Box> tight_node;      // memo, by bvh node index
     std::vector<char> have_h, have_n;
@@ -311,19 +329,21 @@ struct Compiler {
             }
             case RT_HIT_TRANSLATE:
             case RT_HIT_ROTATE_Y: {
-                if (in_xform) {
-                    fail(RT_ERR_UNSUPPORTED, "an instance (Translate/RotateY) nested inside another instance's subtree is not supported by the device layout");
+                if (boundary_in_xform) {
+                    fail(RT_ERR_UNSUPPORTED, "an instance (Translate/RotateY) inside the boundary of a medium that is itself inside an instance is not supported by the device layout");
                     return;
                 }
-                double a[3], b[3], s, c;
-                const int cur = fold_xform(id, a, b, &s, &c);
-                const int w1 = push_box_header(tight(id), make_hdr(OP_XFORM_ENTER));
-                push((float)a[0], (float)a[1], (float)a[2], (float)s);
-                push((float)b[0], (float)b[1], (float)b[2], (float)c);
-                in_xform = true;
+                XfParams X;
+                const int cur = fold_xform(id, X.a, X.b, &X.s, &X.c);       // relative to the enclosing space
+                if (in_xform()) X = compose(xf_stack.back().second, X);     // world -> local
+                const int w1 = push_box_header(tight(id), make_hdr(OP_XFORM_ENTER));   // box in the enclosing space
+                push((float)X.a[0], (float)X.a[1], (float)X.a[2], (float)X.s);
+                push((float)X.b[0], (float)X.b[1], (float)X.b[2], (float)X.c);
+                xf_stack.push_back({w1 - 1, X});
                 emit(cur, in_boundary);
-                in_xform = false;
-                push(0.0f, 0.0f, 0.0f, bits_to_float(make_hdr(OP_XFORM_EXIT)));
+                xf_stack.pop_back();
+                const int parent = in_xform() ? xf_stack.back().first : -1;
+                push(int_to_float_bits(parent), 0.0f, 0.0f, bits_to_float(make_hdr(OP_XFORM_EXIT)));
                 push(0.0f, 0.0f, 0.0f, 0.0f);
                 patch_skip(w1);
                 break;
@@ -333,12 +353,12 @@ struct Compiler {
                 const rt_hittable_desc& bd = d->hittables[h.child];
                 double xa[3], xb[3], xs, xc;
                 const int inner = fold_xform(h.child, xa, xb, &xs, &xc);
-                const bool analytic = bd.kind == RT_HIT_SPHERE || (!in_xform && is_cube(inner));
+                const bool analytic = bd.kind == RT_HIT_SPHERE || (!in_xform() && is_cube(inner));
                 // A world-space medium with an analytic boundary is evaluated once at the start of every segment
                 // instead of at its BVH position: its free-flight draw is keyed by (segment, medium), not by visit
                 // order, and closest-hit is order independent, so the result is the same and every lane of a warp
                 // runs it at the same time.
-                const bool hoist = opt.hoist_media && analytic && !in_xform && (int)hoisted_at.size() < kMaxHoistedMedia;
+                const bool hoist = opt.hoist_media && analytic && !in_xform() && (int)hoisted_at.size() < kMaxHoistedMedia;
                 std::vector<F4> saved;
                 int w1 = -1;
                 if (hoist) { saved.swap(out->ops); hoisted_at.push_back((int32_t)hoisted.size()); }
@@ -352,7 +372,7 @@ struct Compiler {
                     push((float)bd.v0[0], (float)bd.v0[1], (float)bd.v0[2], (float)bd.s0);
                     const uint32_t aux = ((bd.flags & RT_FLAG_MOVING) ? FLAG_MOVING : 0u) | (precise ? FLAG_PRECISE : 0u);
                     push((float)bd.v1[0], (float)bd.v1[1], (float)bd.v1[2], int_to_float_bits((int32_t)(pidx | (aux << 24))));
-                } else if (!in_xform && is_cube(inner)) {
+                } else if (!in_xform() && is_cube(inner)) {
                     const rt_hittable_desc& cube = d->hittables[inner];
                     push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_XBOX)));
                     push((float)xa[0], (float)xa[1], (float)xa[2], (float)xs);
@@ -365,7 +385,10 @@ struct Compiler {
                     push(0.0f, 0.0f, 0.0f, 0.0f);
                     push(0.0f, 0.0f, 0.0f, 0.0f);
                     const int bbegin = here();
+                    const bool was = boundary_in_xform;
+                    boundary_in_xform = was || in_xform();    // the program's rays are local rays: no composed instances inside
                     emit(h.child, true);
+                    boundary_in_xform = was;
                     out->ops[wb].x = int_to_float_bits(bbegin);
                     out->ops[wb].y = int_to_float_bits(here());
                 }
@@ -424,6 +447,7 @@ struct Pruner {
     const std::vector<F4>& in;
     std::vector<F4> out;
     std::unordered_map<uint64_t, std::vector<std::pair<double, double>>> memo;   // at -> [(ancestor area, cost)]
+    std::vector<int> xf_pos;     // emitted positions of the enclosing OP_XFORM_ENTERs (OP_XFORM_EXIT names its parent)
     CompileOptions opt;
     Pruner(const std::vector<F4>& ops, const CompileOptions& o) : in(ops), opt(o) {}
 
@@ -529,10 +553,13 @@ struct Pruner {
             case OP_XFORM_ENTER: {
                 const int pos = (int)out.size();
                 copy_words(n);
+                xf_pos.push_back(pos);
                 emit_list(n.ch, n.area);
+                xf_pos.pop_back();
                 const int exit_at = int_of(in[n.at + 1].w) - 2;
                 out.push_back(in[exit_at]);
                 out.push_back(in[exit_at + 1]);
+                set_int(&out[out.size() - 2].x, xf_pos.empty() ? -1 : (int32_t)xf_pos.back());
                 set_int(&out[pos + 1].w, (int32_t)out.size());
                 return;
             }

@@ -117,7 +117,7 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
     n = len(o)
     end = S.n_world if end is None else end
     o = o.astype(np.float64).copy(); d = d.astype(np.float64).copy()
-    wo, wd = o.copy(), d.copy()                      # the outer ray while inside an instance
+    wo, wd = o.copy(), d.copy()                      # the world ray: instance ops hold composed world -> local transforms
     inv = _safe_inv(d)
     cur_xf = np.full(n, -1, dtype=np.int64)
     idx = np.full(n, begin, dtype=np.int64)
@@ -233,8 +233,8 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
                 idx[r_[~passed]] = skip[~passed]
                 p_ = r_[passed]; ap = a[passed]
                 w2, w3 = F[ap + 2], F[ap + 3]
-                o[p_] = _xform_point(o[p_], w2, w3)
-                d[p_] = _xform_dir(d[p_], w2, w3)
+                o[p_] = _xform_point(wo[p_], w2, w3)
+                d[p_] = _xform_dir(wd[p_], w2, w3)
                 inv[p_] = _safe_inv(d[p_])
                 cur_xf[p_] = ap
                 idx[p_] = ap + 4
@@ -243,8 +243,15 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
         m = kind == OP_XFORM_EXIT
         if m.any():
             r_ = act[m]
-            o[r_] = wo[r_]; d[r_] = wd[r_]; inv[r_] = _safe_inv(d[r_])
-            cur_xf[r_] = -1
+            parent = I[at[m], 0].astype(np.int64)          # the enclosing instance, -1 = world space
+            o[r_] = wo[r_]; d[r_] = wd[r_]
+            nested = parent >= 0
+            if nested.any():
+                q_, pp = r_[nested], parent[nested]
+                o[q_] = _xform_point(wo[q_], F[pp + 2], F[pp + 3])
+                d[q_] = _xform_dir(wd[q_], F[pp + 2], F[pp + 3])
+            inv[r_] = _safe_inv(d[r_])
+            cur_xf[r_] = parent
             idx[r_] = at[m] + 2
         m = kind == OP_SPHERE
         if m.any():

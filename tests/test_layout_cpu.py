@@ -83,16 +83,39 @@ def test_media_inside_instances_stay_in_the_stream(rt):
     assert L["n_medium_in_stream"] == 1 and L["n_medium_hoisted"] == 0 and L["n_xform"] == 1
 
 
-def test_unsupported_nesting_rejected_on_the_host(rt):
+def test_nested_instances_flatten_to_composed_transforms(rt):
+    """An instance inside another instance's subtree: both become OP_XFORM_ENTER ops, the inner one holding the
+    composition (world -> its local space), its OP_XFORM_EXIT naming the outer one as parent."""
     s = rt.Scene()
     m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))
     inner = rt.HittableList()
     inner.add(s.Translate(s.Sphere((0, 0, 0), 1.0, m), (1, 0, 0)))
     inner.add(s.Sphere((3, 0, 0), 1.0, m))
-    s.finish(s.RotateY(s.BVHNode(inner), 10.0))
-    with pytest.raises(rt._abi.RtError) as e:
-        rt.scene_layout(s)
-    assert e.value.status == rt._abi.RT_ERR_UNSUPPORTED
+    s.finish(s.RotateY(s.BVHNode(inner), 90.0))
+    assert rt.scene_layout(s)["n_xform"] == 2
+    ops = rt.scene_ops(s)
+    W, I = ops["words"], ops["words"].view(np.int32).reshape(-1, 4)
+    kinds = I[:ops["n_world_words"], 3] & 15
+    # walk op by op to find the real op starts
+    starts, i = [], 0
+    size = {0: 2, 1: 2, 2: 4, 3: 4, 4: 2, 5: 3, 6: 3, 7: 2}
+    while i < ops["n_world_words"]:
+        starts.append(i)
+        i += size[int(kinds[i])]
+    enter = [i for i in starts if kinds[i] == 3]
+    exits = [i for i in starts if kinds[i] == 4]
+    assert len(enter) == 2 and len(exits) == 2
+    outer, nested = enter
+    assert I[exits[0], 0] == outer and I[exits[1], 0] == -1          # inner exit -> parent, outer exit -> world
+    # composed transform of the nested instance maps the world position of its sphere's centre to the local origin:
+    # RotateY(90 deg) takes local (1, 0, 0) [the translated centre] to world (0, 0, -1) (hittable.rs:173-179)
+    a, sn, b, cs = W[nested + 2, :3], W[nested + 2, 3], W[nested + 3, :3], W[nested + 3, 3]
+    x = np.array([0.0, 0.0, -1.0]) - a
+    local = np.array([cs * x[0] - sn * x[2], x[1], sn * x[0] + cs * x[2]]) + b
+    assert np.allclose(local, 0.0, atol=1e-6)
+
+
+def test_unsupported_nesting_rejected_on_the_host(rt):
     s2 = rt.Scene()
     m2 = s2.Lambertian(s2.SolidColor(0.5, 0.5, 0.5))
     inner_med = s2.ConstantMedium(s2.Sphere((0, 0, 0), 1.0, m2), 0.5, (1, 1, 1))
@@ -100,6 +123,16 @@ def test_unsupported_nesting_rejected_on_the_host(rt):
     with pytest.raises(rt._abi.RtError) as e2:
         rt.scene_layout(s2)
     assert e2.value.status == rt._abi.RT_ERR_UNSUPPORTED
+    s3 = rt.Scene()
+    m3 = s3.Lambertian(s3.SolidColor(0.5, 0.5, 0.5))
+    two = rt.HittableList()
+    two.add(s3.Translate(s3.Sphere((0, 0, 0), 1.0, m3), (1, 0, 0)))
+    two.add(s3.Sphere((0, 2, 0), 1.0, m3))
+    med = s3.ConstantMedium(s3.List(two), 0.5, (1, 1, 1))          # generic boundary holding an instance ...
+    s3.finish(s3.RotateY(med, 20.0))                               # ... inside an instance: the boundary program's rays are local
+    with pytest.raises(rt._abi.RtError) as e3:
+        rt.scene_layout(s3)
+    assert e3.value.status == rt._abi.RT_ERR_UNSUPPORTED
 
 
 @pytest.mark.parametrize("idx", range(9))

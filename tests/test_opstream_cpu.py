@@ -130,3 +130,15 @@ def test_stream_walk_instances_media_and_nesting(rt, ob):
     ref = ob.hit_batch(s.desc, rays, seed=3)
     assert len(set(ref["prim_id"][ref["hit"] == 1])) > 30
     compare(opstream.hit_batch(S, rays, seed=3), ref, max_flips=1)
+
+
+def test_stream_walk_nested_instances(rt, ob):
+    """Instances inside other instances' subtrees, three deep (composed transforms, exits that return to the parent)."""
+    from test_gpu_hits import nested_instances_scene
+    rng = np.random.default_rng(21)
+    s = nested_instances_scene(rt, rng)
+    S = opstream.Stream(rt.scene_ops(s))
+    rays = random_rays(rt, rng, 1 << 15)
+    ref = ob.hit_batch(s.desc, rays, seed=4)
+    assert len(set(ref["prim_id"][ref["hit"] == 1])) > 12
+    compare(opstream.hit_batch(S, rays, seed=4), ref, max_flips=1)

@@ -1,6 +1,7 @@
 """Random scenes for device-vs-oracle parity sweeps (tools/fuzz_parity.py, tests/test_gpu_hits.py): random mixes of
 spheres (static / moving), quads with arbitrary edge vectors (most stick out of the diagonal box Quad::new gives them,
-quad.rs:41-43), cubes, Translate / RotateY instances, BVHs nested in BVHs, lists and media."""
+quad.rs:41-43), cubes, Translate / RotateY instances (also nested in each other's subtrees), BVHs nested in BVHs, lists
+and media."""
 import numpy as np
 
 import rust_tracing_b200 as rt
@@ -13,7 +14,12 @@ def random_scene(seed):
             s.Lambertian(s.CheckerTexture(0.5, (0.1, 0.1, 0.1), (0.9, 0.9, 0.9))), s.DiffuseLight(s.SolidColor(4, 4, 4))]
     pick = lambda: mats[int(rng.integers(0, len(mats)))]
 
-    def prim():
+    def prim(depth=0):
+        if depth < 2 and rng.random() < 0.15:     # an instance of a primitive: nests when the group around it is instanced too
+            inner = prim(depth + 1)
+            if rng.random() < 0.5:
+                inner = s.RotateY(inner, float(rng.uniform(-90, 90)))
+            return s.Translate(inner, rng.uniform(-2, 2, 3))
         k = int(rng.integers(0, 4))
         c = rng.uniform(-8, 8, 3)
         if k == 0:
