@@ -25,8 +25,10 @@ enum OpKind : uint32_t {
     OP_QUAD = 2,         // w0 = {n.xyz, hdr}   w1 = {A.xyz, a0} w2 = {B.xyz, b0} w3 = {d, mat, prim_id, 0}   size 4
                          //   alpha = A.p + a0, beta = B.p + b0 with A = v x w, B = w x u (scalar triple product form of quad.rs:121-122)
     OP_XFORM_ENTER = 3,  // w0 = {lo.xyz, hdr}  w1 = {hi.xyz, skip} w2 = {a.xyz, sin} w3 = {b.xyz, cos}       size 4
-                         //   local = R(x - a) + b, R = rotate-y (hittable.rs:164-168); skip = word after the matching exit
-    OP_XFORM_EXIT = 4,   // w0 = {0,0,0, hdr}   w1 = {0,0,0,0}                           size 2
+                         //   local = R(x - a) + b, R = rotate-y (hittable.rs:164-168), x = the WORLD ray: the transform is the
+                         //   composition with every enclosing instance; the box is in the enclosing space; skip = word after
+                         //   the matching exit
+    OP_XFORM_EXIT = 4,   // w0 = {parent OP_XFORM_ENTER (word index, -1 = world space), 0, 0, hdr}   w1 = {0,0,0,0}   size 2
     OP_MEDIUM = 5,       // body of a ConstantMedium; always preceded by an OP_INNER holding its box (skip = past the medium)
                          // w0 = {neg_inv_density, mat, prim_id, hdr(flags = boundary kind)}
                          //   boundary sphere : w1 = {c.xyz, r}  w2 = {center_vec.xyz, precise_idx | aux<<24}             size 3

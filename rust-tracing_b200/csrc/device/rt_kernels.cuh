@@ -161,7 +161,7 @@ __device__ __forceinline__ bool aabb_hit_reference(float4 w0, float4 w1, float3 
 // a cube's face is recognised by t == plane parameter exactly. With plain operators the two inline sites could get
 // different FMA contractions: a 1-ulp difference then mis-identifies the face, the self-intersection guard of the next
 // segment looks at the wrong plane, and the path re-hits its own surface until max_depth (seen once the instance code
-// was restructured: 8 of 360 000 Cornell paths trapped; the wavefront kernel, compiled separately, was unaffected).
+// was restructured: a handful of 90 000 Cornell paths trapped; the wavefront kernel, compiled separately, was unaffected).
 __device__ __forceinline__ float3 xform_point(float3 x, float4 w2, float4 w3) {
     const float qx = __fsub_rn(x.x, w2.x), qy = __fsub_rn(x.y, w2.y), qz = __fsub_rn(x.z, w2.z);
     const float s = w2.w, c = w3.w;

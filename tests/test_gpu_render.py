@@ -266,7 +266,7 @@ def test_no_trapped_paths_in_instanced_cubes(rt, ob, ctx):
     """A cube's face is recognised by t == plane parameter exactly, with the local ray recomputed in finalize_hit();
     if that recomputation differs by one ulp from the traversal's (different FMA contraction at the two inline sites),
     the face is mis-identified, the next segment's self-intersection guard looks at the wrong plane and the path
-    re-hits its own surface until max_depth. Seen once (8 of 360 000 Cornell paths, +0.06% segments); the instance
+    re-hits its own surface until max_depth. Seen once (a handful of 90 000 Cornell paths, +0.06% segments); the instance
     transforms are now written with explicit rn intrinsics. The device's segment count must be the oracle's."""
     s, cam = small_scene(rt, 6)
     ds = ctx.upload(s)
