@@ -563,13 +563,16 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, 
         const float tx0 = (w0.x - o.x) * inv.x, tx1 = (w1.x - o.x) * inv.x;
         const float ty0 = (w0.y - o.y) * inv.y, ty1 = (w1.y - o.y) * inv.y;
         const float tz0 = (w0.z - o.z) * inv.z, tz1 = (w1.z - o.z) * inv.z;
+        // (nearest rather than equal: t was taken from these very expressions during the traversal and is normally
+        // bit-equal to one of them, but the face must not hinge on two inline sites rounding identically)
         int face = 0;
-        if (tz1 == t) face = 0;
-        if (tx1 == t) face = 1;
-        if (tz0 == t) face = 2;
-        if (tx0 == t) face = 3;
-        if (ty1 == t) face = 4;
-        if (ty0 == t) face = 5;
+        float miss = __int_as_float(0x7f800000);
+        { const float m = fabsf(tz1 - t); if (m <= miss) { miss = m; face = 0; } }
+        { const float m = fabsf(tx1 - t); if (m <= miss) { miss = m; face = 1; } }
+        { const float m = fabsf(tz0 - t); if (m <= miss) { miss = m; face = 2; } }
+        { const float m = fabsf(tx0 - t); if (m <= miss) { miss = m; face = 3; } }
+        { const float m = fabsf(ty1 - t); if (m <= miss) { miss = m; face = 4; } }
+        { const float m = fabsf(ty0 - t); if (m <= miss) { miss = m; face = 5; } }
         const float3 pl = fma3(t, d, o);
         const float ex = 1.0f / (w1.x - w0.x), ey = 1.0f / (w1.y - w0.y), ez = 1.0f / (w1.z - w0.z);
         const float ax = (pl.x - w0.x) * ex, ay = (pl.y - w0.y) * ey, az = (pl.z - w0.z) * ez;   // 0..1 along +x,+y,+z
