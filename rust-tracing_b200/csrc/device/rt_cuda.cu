@@ -711,7 +711,11 @@ static int launch_render_v4(rt_context* c, const rt_scene* s, const rt_camera_de
     c->ms_extend = c->ms_shade = 0.0;
     c->wf_iterations = 0;
 
-    std::vector<cudaEvent_t> tev;   // timing mode: begin / middle / end of every iteration
+    struct EventBag {               // timing mode: begin / middle / end of every iteration; destroyed on every exit path
+        std::vector<cudaEvent_t> v;
+        ~EventBag() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+    } bag;
+    std::vector<cudaEvent_t>& tev = bag.v;
     for (int b = 0;; ++b) {
         unsigned int* live = c->d_live + (b & 1) * kWfBatch;
         prm.live_flag = live;
@@ -747,7 +751,6 @@ static int launch_render_v4(rt_context* c, const rt_scene* s, const rt_camera_de
             c->ms_shade += a;
             c->ms_extend += b2;
         }
-        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return RT_OK;
 }

@@ -142,3 +142,33 @@ def test_stream_walk_nested_instances(rt, ob):
     ref = ob.hit_batch(s.desc, rays, seed=4)
     assert len(set(ref["prim_id"][ref["hit"] == 1])) > 12
     compare(opstream.hit_batch(S, rays, seed=4), ref, max_flips=1)
+
+
+@pytest.mark.parametrize("idx", [0, 6, 7, 8])
+def test_pruning_changes_no_hit(rt, earth, idx, monkeypatch):
+    """prune_stream only removes cull boxes: walked on the same rays, the pruned and the unpruned stream must give
+    bit-identical closest hits (same t, same primitive), and the pruned one must test fewer boxes."""
+    s, cam = small_scene(rt, idx, earth)
+    rays = make_rays(cam, s.desc, 1 << 13, seed=11)
+    pruned = opstream.Stream(rt.scene_ops(s))
+    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
+    full = opstream.Stream(rt.scene_ops(s))
+    ca, cb = {}, {}
+    a = opstream.hit_batch(pruned, rays, seed=11, counts=ca)
+    b = opstream.hit_batch(full, rays, seed=11, counts=cb)
+    assert np.array_equal(a["hit"], b["hit"]) and np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["t"], b["t"])
+    assert ca.get("inner", 0) < cb.get("inner", 0)
+    for k in ("sphere", "quad", "box"):          # leaves are tested at least as often: that is the trade the cost model makes
+        assert ca.get(k, 0) >= cb.get(k, 0)
+
+
+def test_ops_export_argument_checks(rt):
+    import ctypes as C
+    s, _ = small_scene(rt, 1)
+    lib = rt._abi.lib()
+    n = C.c_int64()
+    assert lib.rt_scene_ops_export(None, None, 0, C.byref(n), None, None, None, None) == rt._abi.RT_ERR_INVALID_ARGUMENT
+    assert lib.rt_scene_ops_export(C.byref(s.desc), None, 0, None, None, None, None, None) == rt._abi.RT_ERR_INVALID_ARGUMENT
+    assert lib.rt_scene_ops_export(C.byref(s.desc), None, 0, C.byref(n), None, None, None, None) == 0 and n.value > 2
+    buf = (C.c_float * 8)()
+    assert lib.rt_scene_ops_export(C.byref(s.desc), buf, 2, C.byref(n), None, None, None, None) == rt._abi.RT_ERR_OUT_OF_RANGE
