@@ -110,10 +110,12 @@ def _sphere_roots(oc, d, r):
     return ok, (-hb - sq) / a, (-hb + sq) / a
 
 
-def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None, seg=0, counts=None, visits=None):
+def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None, seg=0, counts=None, visits=None, trace=None):
     """Returns (t, op, xf): closest hit parameter, word index of the winning op (-1 = none) and of its enclosing
     OP_XFORM_ENTER (-1 = world space). `counts`: optional dict kind name -> visits, updated in place; `visits`:
-    optional int64 array over stream words, incremented at the word index of every op a ray executes."""
+    optional int64 array over stream words, incremented at the word index of every op a ray executes; `trace`: optional
+    list that receives one (ray indices, op kinds) pair per lock-step iteration - per ray, in order, the ops it executes
+    (tools/warp_sim.py replays them through the render kernel's warp scheduling)."""
     n = len(o)
     end = S.n_world if end is None else end
     o = o.astype(np.float64).copy(); d = d.astype(np.float64).copy()
@@ -202,6 +204,8 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
         kind = I[at, 3] & 15
         if visits is not None:
             np.add.at(visits, at, 1)
+        if trace is not None:
+            trace.append((act.copy(), kind.astype(np.int8)))
         # ---- box-headed ops: INNER, INNER_REF, XFORM_ENTER, BOX
         for k in (OP_INNER, OP_INNER_REF, OP_XFORM_ENTER, OP_BOX):
             m = kind == k
@@ -296,14 +300,14 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
     return best_t, best_op, best_xf
 
 
-def hit_batch(S, rays, t_min=0.001, t_max=np.inf, seed=7, counts=None, visits=None):
+def hit_batch(S, rays, t_min=0.001, t_max=np.inf, seed=7, counts=None, visits=None, trace=None):
     """The emulated rt_hit_batch: structured array with hit / t / prim_id (the fields the flattening decides)."""
     o = np.ascontiguousarray(rays["origin"], dtype=np.float64)
     d = np.ascontiguousarray(rays["direction"], dtype=np.float64)
     time = np.ascontiguousarray(rays["time"], dtype=np.float64)
     n = len(o)
     key = path_key(seed, np.arange(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32))
-    t, op, xf = traverse(S, o, d, time, t_min, t_max, key=key, seg=0, counts=counts, visits=visits)
+    t, op, xf = traverse(S, o, d, time, t_min, t_max, key=key, seg=0, counts=counts, visits=visits, trace=trace)
     out = np.zeros(n, dtype=[("hit", np.int32), ("t", np.float64), ("prim_id", np.int32)])
     hit = op >= 0
     out["hit"] = hit
