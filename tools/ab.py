@@ -1,6 +1,5 @@
 """A/B timing of kernel variants (development): each variant runs tools/ncu_target.py in a subprocess with
 different RT_B200_* switches and prints Mpaths/s for a few scenes."""
-import itertools
 import os
 import subprocess
 import sys
