@@ -172,3 +172,18 @@ def test_ops_export_argument_checks(rt):
     assert lib.rt_scene_ops_export(C.byref(s.desc), None, 0, C.byref(n), None, None, None, None) == 0 and n.value > 2
     buf = (C.c_float * 8)()
     assert lib.rt_scene_ops_export(C.byref(s.desc), buf, 2, C.byref(n), None, None, None, None) == rt._abi.RT_ERR_OUT_OF_RANGE
+
+
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_pruning_changes_no_hit_random_scenes(rt, seed, monkeypatch):
+    """The same invariant over generated scenes (nested instances, skewed quads whose OP_INNER_REF nodes must survive,
+    media with generic boundaries): pruned and unpruned streams give bit-identical closest hits."""
+    s = random_scene(seed)
+    rays = random_rays(rt, np.random.default_rng(seed), 1 << 12)
+    pruned = opstream.Stream(rt.scene_ops(s))
+    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
+    full = opstream.Stream(rt.scene_ops(s))
+    a = opstream.hit_batch(pruned, rays, seed=seed)
+    b = opstream.hit_batch(full, rays, seed=seed)
+    assert np.array_equal(a["hit"], b["hit"]) and np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["t"], b["t"])
+    assert pruned.n_world <= full.n_world
