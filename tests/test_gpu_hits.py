@@ -26,7 +26,7 @@ UV_TOL = 5e-4
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def check_hits(dev, ref, rays, max_inequivalent=6):
+def check_hits(dev, ref, rays, max_inequivalent=6, t_p99_ulp=T_P99_ULP):
     n = len(ref)
     # a hit/miss flip is only legitimate for a grazing ray; none were observed on 9 x 65536 rays
     flips = int((dev["hit"] != ref["hit"]).sum())
@@ -48,7 +48,7 @@ def check_hits(dev, ref, rays, max_inequivalent=6):
     assert np.array_equal(dev["front_face"][same], ref["front_face"][same])
     if same.any():
         assert t_err[same].max() <= T_MAX_ULP, t_err[same].max()
-        assert np.percentile(t_err[same], 99) <= T_P99_ULP
+        assert np.percentile(t_err[same], 99) <= t_p99_ulp, np.percentile(t_err[same], 99)
         assert n_err[same].max() <= NORMAL_TOL
         du = np.abs(dev["u"] - ref["u"])[same]
         du = np.minimum(du, 1.0 - du)            # sphere u wraps at the seam
@@ -195,6 +195,63 @@ def nested_instances_scene(rt, rng):
     world.add(s.Sphere((0, -12, 0), 3.0, white))
     s.finish(s.BVHNode(world))
     return s
+
+
+def deeply_nested_scene(rt, seed, depth=4):
+    """depth + 1 levels of Translate(RotateY(list or BVH)) each holding three primitives and the next level."""
+    rng = np.random.default_rng(300 + seed)
+    s = rt.Scene(bvh_seed=7 + seed)
+    mats = [s.Lambertian(s.SolidColor(0.6, 0.6, 0.6)), s.Dielectric(1.5), s.Metal((0.8, 0.8, 0.8), 0.1)]
+
+    def level(d):
+        l = rt.HittableList()
+        for _ in range(3):
+            c = rng.uniform(-3, 3, 3)
+            k = int(rng.integers(0, 3))
+            if k == 0:
+                l.add(s.Sphere(c, float(rng.uniform(0.4, 1.0)), mats[int(rng.integers(0, 3))]))
+            elif k == 1:
+                l.add(s.cube(c, c + rng.uniform(0.5, 1.5, 3), mats[0]))
+            else:
+                l.add(s.Quad(c, (float(rng.uniform(0.5, 2)), 0, 0), (0, float(rng.uniform(0.5, 2)), 0), mats[0]))
+        if d > 0:
+            l.add(level(d - 1))
+        g = s.BVHNode(l) if rng.random() < 0.5 else s.List(l)
+        g = s.RotateY(g, float(rng.uniform(-120, 120)))
+        return s.Translate(g, rng.uniform(-2, 2, 3))
+
+    world = rt.HittableList()
+    world.add(level(depth))
+    world.add(s.Sphere((0, -40, 0), 30.0, mats[0]))
+    s.finish(s.BVHNode(world))
+    return s, rng
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_deeply_nested_instances(rt, ob, ctx, seed):
+    """Five levels of instances: composed transforms and exits that return to the parent, on the device."""
+    s, rng = deeply_nested_scene(rt, seed)
+    assert rt.scene_layout(s)["n_xform"] == 5
+    ds = ctx.upload(s)
+    n = 1 << 14
+    rays = np.zeros(n, dtype=rt._abi.ray_dtype())
+    rays["origin"] = rng.uniform(-10, 10, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.5, 2, (n, 1))
+    rays["time"] = rng.random(n)
+    ref = ob.hit_batch(s.desc, rays, seed=1)
+    dev = ctx.hit_batch(ds, rays, seed=1)
+    assert int(ref["hit"].sum()) > 1000
+    # every instance level rotates in f32: the p99 bound is stated per chain of five, not per single instance
+    check_hits(dev, ref, rays, max_inequivalent=4, t_p99_ulp=5 * T_P99_ULP)
+    cs = rt.CameraSettings(image_width=64, aspect_ratio=1.0, samples_per_pixel=4, max_depth=10, vfov=60.0, look_from=(0, 3, 16),
+                           look_at=(0, 0, 0), background=(0.7, 0.8, 1.0))
+    cam = rt.Camera(cs)
+    img = ctx.render(ds, cam, 0, 4, seed=2)
+    want, _ = ob.render(s.desc, cam, 0, 4, seed=2, mode=0)
+    close = np.abs(img[..., :3] - want[..., :3]) <= 1e-3 * np.maximum(1.0, np.abs(want[..., :3]))
+    assert close.all(axis=-1).mean() >= 0.97
+    ds.close()
 
 
 def test_nested_instances(rt, ob, ctx):

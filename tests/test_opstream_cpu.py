@@ -193,31 +193,8 @@ def test_pruning_changes_no_hit_random_scenes(rt, seed, monkeypatch):
 def test_stream_walk_deeply_nested_instances(rt, ob, seed):
     """Five levels of Translate / RotateY around lists and BVHs: the composed world -> local transforms and the parent
     links of the exits must reproduce the oracle's recursive Translate::hit / RotateY::hit (hittable.rs:96-193)."""
-    rng = np.random.default_rng(300 + seed)
-    s = rt.Scene(bvh_seed=7 + seed)
-    mats = [s.Lambertian(s.SolidColor(0.6, 0.6, 0.6)), s.Dielectric(1.5), s.Metal((0.8, 0.8, 0.8), 0.1)]
-
-    def level(depth):
-        l = rt.HittableList()
-        for _ in range(3):
-            c = rng.uniform(-3, 3, 3)
-            k = int(rng.integers(0, 3))
-            if k == 0:
-                l.add(s.Sphere(c, float(rng.uniform(0.4, 1.0)), mats[int(rng.integers(0, 3))]))
-            elif k == 1:
-                l.add(s.cube(c, c + rng.uniform(0.5, 1.5, 3), mats[0]))
-            else:
-                l.add(s.Quad(c, (float(rng.uniform(0.5, 2)), 0, 0), (0, float(rng.uniform(0.5, 2)), 0), mats[0]))
-        if depth > 0:
-            l.add(level(depth - 1))
-        g = s.BVHNode(l) if rng.random() < 0.5 else s.List(l)
-        g = s.RotateY(g, float(rng.uniform(-120, 120)))
-        return s.Translate(g, rng.uniform(-2, 2, 3))
-
-    world = rt.HittableList()
-    world.add(level(4))
-    world.add(s.Sphere((0, -40, 0), 30.0, mats[0]))
-    s.finish(s.BVHNode(world))
+    from test_gpu_hits import deeply_nested_scene
+    s, rng = deeply_nested_scene(rt, seed)
     assert rt.scene_layout(s)["n_xform"] == 5
     S = opstream.Stream(rt.scene_ops(s))
     rays = random_rays(rt, rng, 1 << 14, extent=10.0)
