@@ -16,6 +16,10 @@
 //  * the vote takes a one-ballot fast path while the slab class holds enough lanes;
 //  * the op stream carries two padding words so the next op's words are fetched unconditionally.
 //
+// Since then: the vote takes quorums for minority classes and an exit threshold for the slab repetitions as runtime
+// parameters (their defaults reproduce the rule above: a sweep found nothing better, profiles/r1_ab18*), and the FOLD
+// template parameter lets OP_BOX share OP_INNER's arithmetic (picked per scene by launch_render).
+//
 // Included by rt_cuda.cu.
 #pragma once
 

@@ -4,7 +4,10 @@
 //                    warp owns a pool of (8x4 pixel tile) x (sample chunk) paths; a lane whose path ends takes
 //                    the next path of the pool in the same iteration (ballot/popc ranking); lanes regroup by op
 //                    class through a warp vote. Radiance sums go to a float4 framebuffer, one vector reduction
-//                    per path. render_kernel below is the first, whole-segment-per-iteration form (A/B only).
+//                    per path. Template parameter FOLD: cube primitives share the box-test instruction stream,
+//                    picked per scene (kFoldBoxMin). render_kernel below is the first, whole-segment-per-iteration
+//                    form (A/B only); wf_shade_kernel / wf_extend_kernel (render_v4.cuh) are the same loop as a
+//                    wavefront over a pool of in-flight paths (RT_B200_KERNEL=4: measured, slower, not the product).
 // K2 hit_kernel      Hittable::hit on a ray batch (parity).
 // K3 finalize_kernel color_to_rgb(sum/spp) (color.rs:12-19, renderer.rs:55-58).
 // K4 texture_kernel / get_ray_kernel (parity), expand_image_kernel (upload), fma_peak_kernel.
