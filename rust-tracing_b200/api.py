@@ -206,10 +206,18 @@ def synthetic_earth(width=6400, height=3200, seed=11):
     return img
 
 
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def load_earth(path=None):
-    """Decode the earth image (texture.rs:76-80) with PIL if a path is given or $RT_B200_EARTH /
-    ./assets/earth-large.jpg exists; otherwise return the synthetic stand-in. Returns (array, source)."""
-    candidates = [path, os.environ.get("RT_B200_EARTH"), os.path.join("assets", "earth-large.jpg")]
+    """The decoded earth image (texture.rs:76-80 decodes `assets/earth-large.jpg`, main.rs:179,591), PIL-decoded to
+    RGB8. Looked for, in order: `path`, $RT_B200_EARTH, ./assets/earth-large.jpg, <repo>/assets/earth-large.jpg (the
+    byte copy tools/make_reference_fixtures.py / build() make where the reference checkout exists; it travels to the
+    GPU box) and the reference checkout itself. Only if none exists: the synthetic stand-in, and the source string
+    says so. Returns (array, source)."""
+    candidates = [path, os.environ.get("RT_B200_EARTH"), os.path.join("assets", "earth-large.jpg"),
+                  os.path.join(_REPO_ROOT, "assets", "earth-large.jpg"),
+                  os.path.join(os.environ.get("RT_REFERENCE", "/root/reference"), "assets", "earth-large.jpg")]
     for p in candidates:
         if p and os.path.exists(p):
             from PIL import Image
