@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
         Camera cam(cs);
 
         rt_layout_info info;
-        check(rt_scene_layout(&desc, &info));
+        check(rt_scene_layout(&desc, 0u, &info));
         std::printf("scene: %d hittables, %d bvh nodes -> %d stream words (%d inner, %d quad, %d box, %d instance ops)\n",
                     desc.n_hittables, desc.n_bvh_nodes, info.n_words, info.n_inner, info.n_quad, info.n_box, info.n_xform);
 

@@ -32,7 +32,9 @@
  * (common.rs:1, FP = f64); the device library narrows to f32 at upload.
  * Host memory passed in is owned by the caller and copied; device memory is
  * owned by the handle that allocated it. One context per GPU; a context is
- * used by one host thread at a time.
+ * used by one host thread at a time. A scene keeps its context alive: destroying
+ * the context first is allowed, its memory goes when the last scene does.
+ * The library reads no environment variables.
  */
 #ifndef RT_B200_H
 #define RT_B200_H
@@ -44,7 +46,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -272,6 +274,14 @@ int rt_device_info(rt_context* ctx, int* sm_count, int* sm_clock_khz, size_t* to
 int rt_scene_upload(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out);
 void rt_scene_destroy(rt_scene* scene);
 
+/* Switches of the flattening, for tests and A/B runs (0 = the product's layout). Every combination renders the same
+ * image: they only change how the device walks the scene. */
+#define RT_LAYOUT_NO_PRUNE 1u           /* keep every cull box of the reference's BVH (no prune_stream) */
+#define RT_LAYOUT_NO_BOX_PRIMITIVES 2u  /* Quad::cube lists stay six quads */
+#define RT_LAYOUT_NO_HOIST 4u           /* media stay at their BVH position */
+#define RT_LAYOUT_OPS_IN_GLOBAL 8u      /* the render kernel reads the op stream from global memory, not from shared memory */
+int rt_scene_upload_ex(rt_context* ctx, const rt_scene_desc* desc, uint32_t layout_flags, rt_scene** out);
+
 /* What rt_scene_upload would build for this description, computed on the host (no GPU needed): sizes of the device
  * layout and how many ops of each kind the flattened traversal stream holds. Fails with the same status as
  * rt_scene_upload for descriptions the device layout cannot express (RT_ERR_UNSUPPORTED) or that are malformed. */
@@ -282,19 +292,23 @@ typedef struct rt_layout_info {
     int32_t n_bvh;              /* BVH hittables reachable from the world */
     int64_t device_bytes;       /* op stream + materials + textures + Perlin tables + image texels (float4) */
 } rt_layout_info;
-int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out);
+int rt_scene_layout(const rt_scene_desc* desc, uint32_t layout_flags, rt_layout_info* out);
 
 /* The flattened traversal stream itself, as rt_scene_upload would place it in HBM (host dry run, no GPU): float4
  * words (4 floats each; headers and links are integers stored bit-for-bit), the world program in [0, n_world_words),
  * hoisted media bodies behind it. words may be NULL to query *n_total_words. media_ops receives the word indices of
- * the hoisted media (capacity 8). Lets a host-side check walk exactly what the kernels walk (tests/opstream.py). */
-int rt_scene_ops_export(const rt_scene_desc* desc, float* words, int64_t capacity_words, int64_t* n_total_words,
-                        int32_t* n_world_words, int32_t* media_ops, int32_t* n_media, int32_t* first_class);
+ * the hoisted media (capacity 8), *first_link the link of op 0 (byte offset | op class << 28). Lets a host-side check
+ * walk exactly what the kernels walk (tests/opstream.py). */
+int rt_scene_ops_export(const rt_scene_desc* desc, uint32_t layout_flags, float* words, int64_t capacity_words, int64_t* n_total_words,
+                        int32_t* n_world_words, int32_t* media_ops, int32_t* n_media, uint32_t* first_link);
 
 /* Render samples [sample_begin, sample_begin+sample_count) of every pixel and ADD the
  * per-pixel sums into a device float4 buffer (x,y,z = radiance sum, w = sample count),
- * W*H elements row-major (pos = j*W + i, renderer.rs:32-33). Asynchronous on `stream`
- * (a cudaStream_t, NULL = default stream). */
+ * W*H elements row-major (pos = j*W + i, renderer.rs:32-33), 16-byte aligned. Asynchronous on
+ * `stream` (a cudaStream_t, NULL = default stream). The sample range must lie in [0, 2^32) (the
+ * RNG key takes the sample index as 32 bits). Launches on different streams of one context may be
+ * in flight together (each takes its own work counter; up to 64 at a time); calls into one context
+ * still come from one host thread at a time. */
 int rt_render_accumulate(rt_context* ctx, const rt_scene* scene, const rt_camera_desc* cam,
                          int64_t sample_begin, int64_t sample_count, uint64_t seed,
                          void* d_sum_rgba, void* stream);
@@ -305,11 +319,18 @@ int rt_render(rt_context* ctx, const rt_scene* scene, const rt_camera_desc* cam,
               int64_t sample_begin, int64_t sample_count, uint64_t seed, float* host_sum_rgba);
 
 /* color_to_rgb(sum/spp) for every pixel (color.rs:12-19, renderer.rs:55-58): device float4
- * sums -> host RGB8, W*H*3 bytes. spp <= 0: divide by the w channel instead. */
+ * sums -> host RGB8, W*H*3 bytes. spp <= 0: divide by the w channel instead. Runs on `stream`
+ * (pass the stream the framebuffer was rendered on: the kernel is then ordered after those
+ * launches) and returns when the bytes are in host memory. */
 int rt_finalize_rgb8(rt_context* ctx, const void* d_sum_rgba, int64_t n_pixels, double spp,
-                     uint8_t* host_rgb8);
+                     uint8_t* host_rgb8, void* stream);
 
-/* Statistics of the last rt_render_accumulate on this context (after synchronisation). */
+/* renderer.rs:26-58 end to end on the device: render the range into the context's framebuffer, then
+ * color_to_rgb(sum / sample_count) there; only the W*H*3 RGB8 bytes cross to the host (what `-o name` writes). */
+int rt_render_rgb8(rt_context* ctx, const rt_scene* scene, const rt_camera_desc* cam,
+                   int64_t sample_begin, int64_t sample_count, uint64_t seed, uint8_t* host_rgb8);
+
+/* Statistics of the last rt_render_accumulate on this context; waits for the device to go idle first. */
 typedef struct rt_render_stats {
     uint64_t paths;
     uint64_t segments;      /* world.hit calls (one per bounce) */
@@ -317,11 +338,6 @@ typedef struct rt_render_stats {
     float last_kernel_ms;   /* 0 unless timing was enabled */
 } rt_render_stats;
 int rt_render_get_stats(rt_context* ctx, rt_render_stats* out);
-
-/* Profiling runs only: with RT_B200_TIMING=1 in the environment at rt_context_create, every kernel launch of a render
- * is bracketed by CUDA events on the launching stream. Returns the summed durations of the last render's shade and
- * extend launches (render_v4.cuh) and the number of shade/extend iterations enqueued (all zero without timing). */
-int rt_render_get_kernel_times(rt_context* ctx, double* ms_shade, double* ms_extend, uint64_t* iterations);
 
 /* Instrumented run of the same kernel: counts the ops the device traversal executes (box tests, sphere tests,
  * quad tests, shades by material, ...) over the given sample range. counters[] receives the counts (returns how

@@ -39,7 +39,7 @@ def main(argv=None):
     t0 = time.time()
     if args.live:
         from rust_tracing_b200.live import ProgressiveRender
-        prog = ProgressiveRender(ctx, ds, cam, seed=args.seed)
+        prog = ProgressiveRender(ctx, ds, cam, seed=args.seed, scene=s)
         frame = None
         for n, frame in prog.frames():
             if n % 16 == 0:
@@ -48,12 +48,12 @@ def main(argv=None):
         if frame is not None:
             Image.fromarray(frame).save(f"{args.output}.png")
     else:
-        sums = ctx.render(ds, cam, 0, cam.samples_per_pixel, args.seed)
+        rgb = ctx.render_rgb8(ds, cam, 0, cam.samples_per_pixel, args.seed)   # sums stay on the device; color_to_rgb runs there
         dt = time.time() - t0
         h, w = cam.shape
         print(f"Render time: {dt:.2f}s ({h * w * cam.samples_per_pixel / dt / 1e6:.1f} Mpaths/s)")   # renderer.rs:51
         t0 = time.time()
-        Image.fromarray(rt.color_to_rgb8(sums, cam.samples_per_pixel)).save(f"{args.output}.png")
+        Image.fromarray(rgb).save(f"{args.output}.png")
         print(f"PNG encoding: {time.time() - t0:.2f}s")      # renderer.rs:73
     return 0
 

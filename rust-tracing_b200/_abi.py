@@ -25,6 +25,7 @@ RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT
  RT_HIT_CONSTANT_MEDIUM, RT_HIT_BVH) = range(7)
 RT_FLAG_MOVING = 1
 RT_FLAG_CUBE_LIST = 2
+RT_LAYOUT_NO_PRUNE, RT_LAYOUT_NO_BOX_PRIMITIVES, RT_LAYOUT_NO_HOIST, RT_LAYOUT_OPS_IN_GLOBAL = 1, 2, 4, 8
 
 d3 = C.c_double * 3
 d6 = C.c_double * 6
@@ -163,14 +164,15 @@ PROTOTYPES = {
     "rt_device_info": (C.c_int, [vp, P(C.c_int), P(C.c_int), P(C.c_size_t)]),
     "rt_scene_upload": (C.c_int, [vp, P(SceneDesc), P(vp)]),
     "rt_scene_destroy": (None, [vp]),
-    "rt_scene_layout": (C.c_int, [P(SceneDesc), P(LayoutInfo)]),
-    "rt_scene_ops_export": (C.c_int, [P(SceneDesc), P(C.c_float), C.c_int64, P(C.c_int64), P(C.c_int32), P(C.c_int32),
-                                      P(C.c_int32), P(C.c_int32)]),
+    "rt_scene_upload_ex": (C.c_int, [vp, P(SceneDesc), C.c_uint32, P(vp)]),
+    "rt_scene_layout": (C.c_int, [P(SceneDesc), C.c_uint32, P(LayoutInfo)]),
+    "rt_scene_ops_export": (C.c_int, [P(SceneDesc), C.c_uint32, P(C.c_float), C.c_int64, P(C.c_int64), P(C.c_int32), P(C.c_int32),
+                                      P(C.c_int32), P(C.c_uint32)]),
     "rt_render_accumulate": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp, vp]),
     "rt_render": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp]),
-    "rt_finalize_rgb8": (C.c_int, [vp, vp, C.c_int64, C.c_double, vp]),
+    "rt_render_rgb8": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp]),
+    "rt_finalize_rgb8": (C.c_int, [vp, vp, C.c_int64, C.c_double, vp, vp]),
     "rt_render_get_stats": (C.c_int, [vp, P(RenderStats)]),
-    "rt_render_get_kernel_times": (C.c_int, [vp, P(C.c_double), P(C.c_double), P(C.c_uint64)]),
     "rt_render_count_ops": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp, C.c_int, P(C.c_char_p)]),
     "rt_hit_batch": (C.c_int, [vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_uint64, vp]),
     "rt_texture_batch": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, vp]),

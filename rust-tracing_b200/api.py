@@ -254,33 +254,39 @@ def builtin_scene(scene, image_width=0, samples_per_pixel=0, max_depth=0, scene_
     return s, settings
 
 
-def scene_layout(scene):
+def layout_flags(prune=True, box_primitives=True, hoist_media=True, ops_in_smem=True):
+    """RT_LAYOUT_* switches of the flattening (tests and A/B runs; the defaults are the product's layout)."""
+    return ((0 if prune else A.RT_LAYOUT_NO_PRUNE) | (0 if box_primitives else A.RT_LAYOUT_NO_BOX_PRIMITIVES) |
+            (0 if hoist_media else A.RT_LAYOUT_NO_HOIST) | (0 if ops_in_smem else A.RT_LAYOUT_OPS_IN_GLOBAL))
+
+
+def scene_layout(scene, flags=0):
     """Host-side dry run of the flattening rt_scene_upload performs (no GPU): dict of op counts and sizes."""
     info = A.LayoutInfo()
-    A.check(A.lib().rt_scene_layout(C.byref(scene.desc), C.byref(info)))
+    A.check(A.lib().rt_scene_layout(C.byref(scene.desc), flags, C.byref(info)))
     return {name: getattr(info, name) for name, _ in A.LayoutInfo._fields_}
 
 
-def scene_ops(scene):
+def scene_ops(scene, flags=0):
     """rt_scene_ops_export: the flattened traversal stream (host dry run). Returns a dict with `words` (float32 (N, 4)),
-    `n_world_words`, `media_ops` (word indices of the hoisted media) and `first_class`."""
+    `n_world_words`, `media_ops` (word indices of the hoisted media) and `first_link` (link of op 0)."""
     lib = A.lib()
-    n, nw, nm, fc = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+    n, nw, nm, fl = C.c_int64(), C.c_int32(), C.c_int32(), C.c_uint32()
     media = (C.c_int32 * 8)()
-    A.check(lib.rt_scene_ops_export(C.byref(scene.desc), None, 0, C.byref(n), None, None, None, None))
+    A.check(lib.rt_scene_ops_export(C.byref(scene.desc), flags, None, 0, C.byref(n), None, None, None, None))
     words = np.zeros((n.value, 4), dtype=np.float32)
-    A.check(lib.rt_scene_ops_export(C.byref(scene.desc), words.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n),
-                                    C.byref(nw), media, C.byref(nm), C.byref(fc)))
+    A.check(lib.rt_scene_ops_export(C.byref(scene.desc), flags, words.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n),
+                                    C.byref(nw), media, C.byref(nm), C.byref(fl)))
     return {"words": words, "n_world_words": nw.value, "media_ops": [int(media[k]) for k in range(nm.value)],
-            "first_class": fc.value}
+            "first_link": fl.value}
 
 
 class DeviceScene:
-    def __init__(self, ctx, scene):
+    def __init__(self, ctx, scene, flags=0):
         self.ctx = ctx
         self._lib = A.lib()
         h = C.c_void_p()
-        A.check(self._lib.rt_scene_upload(ctx._h, C.byref(scene.desc), C.byref(h)))
+        A.check(self._lib.rt_scene_upload_ex(ctx._h, C.byref(scene.desc), flags, C.byref(h)))
         self._h = h
 
     def close(self):
@@ -321,8 +327,8 @@ class Context:
         A.check(self._lib.rt_device_info(self._h, C.byref(sm), C.byref(khz), C.byref(mem)))
         return {"sm_count": sm.value, "sm_clock_khz": khz.value, "total_mem": mem.value}
 
-    def upload(self, scene):
-        return DeviceScene(self, scene)
+    def upload(self, scene, flags=0):
+        return DeviceScene(self, scene, flags)
 
     def render(self, dscene, cam, sample_begin=0, sample_count=None, seed=0):
         """rt_render: host float32 (H, W, 4) sums (x,y,z radiance, w sample count)."""
@@ -334,14 +340,25 @@ class Context:
                                     out.ctypes.data))
         return out
 
+    def render_rgb8(self, dscene, cam, sample_begin=0, sample_count=None, seed=0):
+        """rt_render_rgb8: render + device-side color_to_rgb(sum/spp); host uint8 (H, W, 3)."""
+        if sample_count is None:
+            sample_count = cam.samples_per_pixel
+        h, w = cam.shape
+        out = np.empty((h, w, 3), dtype=np.uint8)
+        A.check(self._lib.rt_render_rgb8(self._h, dscene._h, C.byref(cam), sample_begin, sample_count, seed, out.ctypes.data))
+        return out
+
     def render_accumulate(self, dscene, cam, sample_begin, sample_count, seed, d_sum_ptr, stream=0):
         """rt_render_accumulate into a device float4 buffer (e.g. a torch tensor's data_ptr())."""
         A.check(self._lib.rt_render_accumulate(self._h, dscene._h, C.byref(cam), sample_begin, sample_count,
                                                seed, C.c_void_p(d_sum_ptr), C.c_void_p(stream)))
 
-    def finalize_rgb8(self, d_sum_ptr, n_pixels, spp):
+    def finalize_rgb8(self, d_sum_ptr, n_pixels, spp, stream=0):
+        """rt_finalize_rgb8 on `stream` (the stream the framebuffer was rendered on)."""
         out = np.empty((n_pixels, 3), dtype=np.uint8)
-        A.check(self._lib.rt_finalize_rgb8(self._h, C.c_void_p(d_sum_ptr), n_pixels, float(spp), out.ctypes.data))
+        A.check(self._lib.rt_finalize_rgb8(self._h, C.c_void_p(d_sum_ptr), n_pixels, float(spp), out.ctypes.data,
+                                           C.c_void_p(stream)))
         return out
 
     def stats(self):
@@ -349,12 +366,6 @@ class Context:
         A.check(self._lib.rt_render_get_stats(self._h, C.byref(st)))
         return {"paths": st.paths, "segments": st.segments, "kernel_launches": st.kernel_launches,
                 "last_kernel_ms": st.last_kernel_ms}
-
-    def kernel_times(self):
-        """Summed shade / extend launch durations of the last render (needs RT_B200_TIMING=1 at context creation)."""
-        a, b, n = C.c_double(), C.c_double(), C.c_uint64()
-        A.check(self._lib.rt_render_get_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
-        return {"ms_shade": a.value, "ms_extend": b.value, "iterations": n.value}
 
     def count_ops(self, dscene, cam, sample_begin=0, sample_count=1, seed=0):
         """Op counts of the instrumented kernel over a sample range (dict name -> count)."""
@@ -419,15 +430,17 @@ def color_to_rgb8(sums, spp):
 
 def render(camera, world, output_file_name=None, seed=0, device_id=0):
     """Drop-in for `pub fn render(camera, world, output_file_name)` (renderer.rs:12): renders
-    camera.samples_per_pixel samples per pixel on the GPU and returns the (H, W, 3) float32 SUM
-    image; if output_file_name is given, writes `<name>.png` like renderer.rs:53-74."""
+    camera.samples_per_pixel samples per pixel on the GPU. With output_file_name it writes `<name>.png` like
+    renderer.rs:53-74 (the bytes come from the device, rt_render_rgb8) and returns the (H, W, 3) uint8 image;
+    without, it returns the (H, W, 3) float32 SUM image of renderer.rs:26-49."""
     ctx = default_context(device_id)
     ds = ctx.upload(world)
     try:
-        sums = ctx.render(ds, camera, 0, camera.samples_per_pixel, seed)
+        if output_file_name:
+            from PIL import Image
+            rgb = ctx.render_rgb8(ds, camera, 0, camera.samples_per_pixel, seed)
+            Image.fromarray(rgb).save(f"{output_file_name}.png")
+            return rgb
+        return ctx.render(ds, camera, 0, camera.samples_per_pixel, seed)[..., :3]
     finally:
         ds.close()
-    if output_file_name:
-        from PIL import Image
-        Image.fromarray(color_to_rgb8(sums, camera.samples_per_pixel)).save(f"{output_file_name}.png")
-    return sums[..., :3]

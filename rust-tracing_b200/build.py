@@ -22,8 +22,7 @@ DEPS = SOURCES + [
     os.path.join(CSRC, "host", "host_rng.h"),
     os.path.join(CSRC, "device", "dev_scene.h"),
     os.path.join(CSRC, "device", "rt_kernels.cuh"),
-    os.path.join(CSRC, "device", "render_v3.cuh"),
-    os.path.join(CSRC, "device", "render_v4.cuh"),
+    os.path.join(CSRC, "device", "render_mk.cuh"),
     os.path.join(HERE, "..", "include", "rt_b200.h"),
     os.path.join(HERE, "..", "include", "rt_b200.hpp"),
 ]

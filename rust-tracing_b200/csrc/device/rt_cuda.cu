@@ -1,16 +1,13 @@
 // Kernels + device half of the C ABI (include/rt_b200.h).
 //
-// K1 render_kernel_v3 (render_v3.cuh): persistent megakernel for the parallel loop of renderer.rs:26-49. One
-//                    warp owns a pool of (8x4 pixel tile) x (sample chunk) paths; a lane whose path ends takes
-//                    the next path of the pool in the same iteration (ballot/popc ranking); lanes regroup by op
-//                    class through a warp vote. Radiance sums go to a float4 framebuffer, one vector reduction
-//                    per path. Template parameter FOLD: cube primitives share the box-test instruction stream,
-//                    picked per scene (kFoldBoxMin). render_kernel below is the first, whole-segment-per-iteration
-//                    form (A/B only); wf_shade_kernel / wf_extend_kernel (render_v4.cuh) are the same loop as a
-//                    wavefront over a pool of in-flight paths (RT_B200_KERNEL=4: measured, slower, not the product).
+// K1 render_kernel_mk (render_mk.cuh): persistent megakernel for the parallel loop of renderer.rs:26-49, one CTA per SM.
+//                    The op stream is staged in shared memory by a bulk (TMA) copy; one warp owns a pool of (8x4 pixel
+//                    tile) x (sample chunk) paths; a lane whose path ends takes the next path of the pool in the same
+//                    iteration (ballot/popc ranking); lanes regroup by op class through a warp vote. Radiance sums go to
+//                    a float4 framebuffer, one vector reduction per path.
 // K2 hit_kernel      Hittable::hit on a ray batch (parity).
 // K3 finalize_kernel color_to_rgb(sum/spp) (color.rs:12-19, renderer.rs:55-58).
-// K4 texture_kernel / get_ray_kernel (parity), expand_image_kernel (upload), fma_peak_kernel.
+// K4 texture_kernel / get_ray_kernel / scatter_kernel (parity), expand_image_kernel (upload), fma_peak_kernel.
 #include "rt_kernels.cuh"
 
 #include "../host/host_common.h"
@@ -21,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace rtdev;
@@ -28,11 +26,6 @@ using rt_host::fail;
 
 namespace {
 
-#ifdef RT_OPT_BLOCK
-constexpr int kBlockThreads = RT_OPT_BLOCK;
-#else
-constexpr int kBlockThreads = 128;
-#endif
 constexpr int kTileW = 8, kTileH = 4;
 constexpr int kMaxPerlinShared = 4;
 
@@ -48,12 +41,11 @@ struct RenderParams {
     float4* sum;          // W*H float4
     unsigned int* work_counter;
     unsigned long long* stats;   // [0] paths, [1] segments, [2..] op counters (counting build only)
-    int first_class;             // OpClass of op 0
+    uint32_t first_link;         // link of op 0 (dev_scene.h)
+    uint32_t ops_bytes;          // bytes of the op stream staged in shared memory (0: read from global memory)
     int shade_min;               // the shade class may win the vote once this many lanes wait for it
-    int slab_fast;               // v3: lanes in the slab class that skip the full vote
-    int slab_reps, sphere_reps;  // v3: consecutive ops a class may run per vote (slab: compile-time kSlabReps)
-    int slab_exit;               // v3: the slab repetitions stop (and the warp votes again) once fewer lanes than this remain in the class
-    int sphere_min, box_min, quad_min;   // v3: quorum at which a minority class runs ahead of the slab class
+    int slab_fast;               // lanes in the slab class that skip the full vote
+    int sphere_reps;             // consecutive sphere ops per vote
 };
 
 // op counters of the instrumented kernel (rt_render_count_ops): what the device traversal actually executes
@@ -75,116 +67,10 @@ __device__ __forceinline__ void stage_perlin(const DevScene& S, float4* sh_vec, 
     __syncthreads();
 }
 
-extern __shared__ float4 dyn_smem[];
+__device__ __forceinline__ void set_ops_base(OpsGlobal& o, const float4* g) { o.base = g; }
+__device__ __forceinline__ void set_ops_base(OpsShared&, const float4*) {}
 
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParams prm) {
-    float4* sh_vec = dyn_smem;
-    uint8_t* sh_perm = reinterpret_cast<uint8_t*>(dyn_smem + kMaxPerlinShared * 256);
-    stage_perlin(prm.scene, sh_vec, sh_perm);
-    PerlinShared P{sh_vec, sh_perm};
-    const DevScene& S = prm.scene;
-    const DevCamera& C = prm.cam;
-
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned n_tiles = (unsigned)(prm.tiles_x * prm.tiles_y);
-    const unsigned n_items = n_tiles * (unsigned)prm.n_chunks;
-
-    // warp-uniform pool state
-    int pool_next = 0, pool_size = 0;
-    int tile_x0 = 0, tile_y0 = 0, tile_w = 1, tile_n = 1;
-    int64_t pool_sample0 = 0;
-    bool no_more = false;
-
-    // per-lane path state
-    bool active = false;
-    Ray ray;
-    float3 L, T;
-    int depth = 0, origin = -1, pix = 0;
-    uint4 key;
-    unsigned long long n_paths = 0, n_segments = 0;
-
-    for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, !active);
-        if (need) {
-            if (pool_next >= pool_size && !no_more) {
-                unsigned item = 0;
-                if (lane == 0) item = atomicAdd(prm.work_counter, 1u);
-                item = __shfl_sync(0xffffffffu, item, 0);
-                if (item >= n_items) {
-                    no_more = true;
-                } else {
-                    const unsigned chunk_idx = item / n_tiles, tile = item % n_tiles;   // chunk-major: concurrent warps spread over tiles
-                    tile_x0 = (int)(tile % (unsigned)prm.tiles_x) * kTileW;
-                    tile_y0 = (int)(tile / (unsigned)prm.tiles_x) * kTileH;
-                    tile_w = min(kTileW, C.width - tile_x0);
-                    const int tile_h = min(kTileH, C.height - tile_y0);
-                    tile_n = tile_w * tile_h;
-                    const int s0 = (int)chunk_idx * prm.chunk;
-                    const int ns = min(prm.chunk, prm.sample_count - s0);
-                    pool_sample0 = prm.sample_begin + s0;
-                    pool_size = tile_n * ns;
-                    pool_next = 0;
-                }
-            }
-            if (!active) {
-                const int idx = pool_next + __popc(need & lt_mask);
-                if (idx < pool_size) {
-                    const int pv = idx % tile_n, sv = idx / tile_n;
-                    const int px = tile_x0 + pv % tile_w, py = tile_y0 + pv / tile_w;
-                    pix = py * C.width + px;                                         // renderer.rs:32-33
-                    key = path_key(prm.seed, (uint32_t)pix, (uint32_t)(pool_sample0 + sv));
-                    ray = camera_ray(C, px, py, key);
-                    L = f3(0.0f, 0.0f, 0.0f);
-                    T = f3(1.0f, 1.0f, 1.0f);
-                    depth = 0;
-                    origin = -1;
-                    active = true;
-                    ++n_paths;
-                }
-            }
-            pool_next = min(pool_size, pool_next + __popc(need));
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u) {
-            if (no_more) break;
-            continue;
-        }
-        if (active) {
-            // one bounce of ray_color (renderer.rs:139-155), iteratively
-            ++n_segments;
-            Best best;
-            traverse<true>(S, 0, S.n_words, ray, 0.001f, __int_as_float(0x7f800000), best, origin, key, (uint32_t)depth);
-            bool alive;
-            if (best.op < 0) {
-                L = L + T * C.background;                                            // renderer.rs:152-153
-                alive = false;
-            } else {
-                HitRec h;
-                finalize_hit(S, ray, best, h);
-                alive = shade(S, P, ray, h, key, (uint32_t)depth, L, T);
-                origin = h.origin;
-                ++depth;
-                if (depth >= C.max_depth) alive = false;                             // depth <= 0 returns black (:140-142)
-            }
-            if (!alive) {
-                red_add_f4(prm.sum + pix, L.x, L.y, L.z, 1.0f);                      // avg_color += new_color (:39)
-                active = false;
-            }
-        }
-    }
-    // stats: one atomic per warp
-    for (int off = 16; off > 0; off >>= 1) {
-        n_paths += __shfl_down_sync(0xffffffffu, n_paths, off);
-        n_segments += __shfl_down_sync(0xffffffffu, n_segments, off);
-    }
-    if (lane == 0) {
-        atomicAdd(prm.stats + 0, n_paths);
-        atomicAdd(prm.stats + 1, n_segments);
-    }
-}
-
-#include "render_v3.cuh"
-#include "render_v4.cuh"
+#include "render_mk.cuh"
 
 struct DevRayIn { float ox, oy, oz, dx, dy, dz, time, pad; };
 struct DevHitOut { float t, px, py, pz, nx, ny, nz, u, v; int hit, front_face, prim, mat; };
@@ -197,13 +83,14 @@ __global__ void hit_kernel(DevScene S, const DevRayIn* rays, int64_t n, float tm
     ray.o = f3(r.ox, r.oy, r.oz); ray.d = f3(r.dx, r.dy, r.dz); ray.time = r.time;
     Best best;
     const uint4 key = path_key(seed, (uint32_t)k, 0u);
-    traverse<true>(S, 0, S.n_words, ray, tmin, tmax, best, -1, key, 0u);
+    const OpsGlobal ops{S.ops};
+    traverse<true>(S, ops, 0, S.n_words, ray, tmin, tmax, best, -1, key, 0u);
     DevHitOut o;
     memset(&o, 0, sizeof(o));
     o.prim = -1; o.mat = -1;
     if (best.op >= 0) {
         HitRec h;
-        finalize_hit(S, ray, best, h);
+        finalize_hit(S, ops, ray, best, h);
         if (h.uv_lazy) sphere_uv(h.sn, &h.u, &h.v);
         o.hit = 1; o.t = h.t;
         o.px = h.p.x; o.py = h.p.y; o.pz = h.p.z;
@@ -303,100 +190,110 @@ DevCamera make_dev_camera(const rt_camera_desc& c) {
 }  // namespace
 
 typedef void (*render_fn)(const RenderParams);
-static render_fn v3_kernel(bool counting, int min_blocks, bool fold) {
-    if (counting) return render_kernel_v3<true, 1, false>;
-    if (fold) {
-        switch (min_blocks) {
-            case 5: return render_kernel_v3<false, 5, true>;
-            case 4: return render_kernel_v3<false, 4, true>;
-            default: return render_kernel_v3<false, 6, true>;
-        }
-    }
-    switch (min_blocks) {
-        case 8: return render_kernel_v3<false, 8, false>;
-        case 7: return render_kernel_v3<false, 7, false>;
-        case 3: return render_kernel_v3<false, 3, false>;
-        case 2: return render_kernel_v3<false, 2, false>;
-        case 6: return render_kernel_v3<false, 6, false>;
-        case 5: return render_kernel_v3<false, 5, false>;
-        default: return render_kernel_v3<false, 4, false>;
-    }
+static render_fn mk_kernel(bool counting, bool ops_smem) {
+    if (counting) return ops_smem ? render_kernel_mk<true, true> : render_kernel_mk<true, false>;
+    return ops_smem ? render_kernel_mk<false, true> : render_kernel_mk<false, false>;
 }
-constexpr int kFoldBoxMin = 64;   // scenes with at least this many cube primitives run the FOLD form of the kernel (render_v3.cuh)
 
-typedef void (*wf_extend_fn)(const WfParams);
-typedef void (*wf_shade_fn)(const WfParams, const int);
-static wf_extend_fn wf_extend(int min_blocks) {
-    switch (min_blocks) {
-        case 12: return wf_extend_kernel<12>;
-        case 10: return wf_extend_kernel<10>;
-        case 6: return wf_extend_kernel<6>;
-        case 5: return wf_extend_kernel<5>;
-        case 4: return wf_extend_kernel<4>;
-        default: return wf_extend_kernel<8>;
-    }
-}
-static wf_shade_fn wf_shade(int min_blocks) {
-    switch (min_blocks) {
-        case 8: return wf_shade_kernel<8>;
-        case 6: return wf_shade_kernel<6>;
-        case 3: return wf_shade_kernel<3>;
-        default: return wf_shade_kernel<4>;
-    }
-}
-constexpr int kWfBatch = 16;   // iterations enqueued between two looks at the live flag
+// rt_render_accumulate may be called on several streams of one context: every launch takes its own work counter and
+// statistics block from a ring, zeroed on the launching stream, so launches in flight never share them.
+constexpr int kLaunchSlots = 64;
+constexpr size_t kStagingBytes = 8u << 20;   // two pinned buffers of this size carry host -> device uploads
 
 struct rt_context {
-    // wavefront renderer (render_v4.cuh): pool of in-flight paths and its bookkeeping
-    WavePool pool{};
-    size_t pool_capacity = 0;
-    int pool_slots = 1 << 20;    // 5 x 16 B per slot = 80 MB: stays in the 126 MB L2 between the two kernels
-    int wf_extend_blocks = 8, wf_shade_blocks = 4, wf_fetch_min = 6, wf_slab_fast = 14;
-    unsigned long long* d_path_counter = nullptr;
-    unsigned int* d_slot_cursor = nullptr;
-    unsigned int* d_live = nullptr;          // 2 x kWfBatch flags
-    unsigned int* h_live = nullptr;          // pinned, 2 flags
-    ulonglong2* d_reserve = nullptr;
-    size_t reserve_warps = 0;
-    cudaEvent_t wf_event[2] = {nullptr, nullptr};
-    bool timing = false;                     // RT_B200_TIMING: CUDA events around every launch (profiling runs only)
-    double ms_extend = 0.0, ms_shade = 0.0;  // of the last render, timing mode only
-    uint64_t wf_iterations = 0;
     int device = 0;
     int sm_count = 0;
     int clock_khz = 0;
     size_t total_mem = 0;
-    int blocks_per_sm = 1;       // of the selected production kernel
-    int variant = 3;             // 4: wavefront (render_v4.cuh); 3: megakernel (render_v3.cuh); 1: whole-segment loop (A/B only)
-    int min_blocks = 6;          // occupancy variant: resident 128-thread blocks per SM the kernel is compiled for
-    bool hoist_media = true;
-    int shade_min = 24;
-    int slab_fast = 14, slab_reps = 8, sphere_reps = 2;
-    int slab_exit = 1, sphere_min = 33, box_min = 33, quad_min = 33;
-    bool box_class = false;
-    int fold_box = -1;           // -1: per scene (kFoldBoxMin); 0 / 1 forced (RT_B200_FOLD_BOX, A/B runs)
-    bool prune_boxes = true;
-    bool box_primitives = true;
-    unsigned int* d_counter = nullptr;
-    unsigned long long* d_stats = nullptr;
-    float4* d_fb = nullptr;
+    size_t smem_optin = 0;       // largest dynamic shared memory a CTA may ask for
+    // vote parameters of the render kernel (render_mk.cuh) and layout options; the product never reads the environment,
+    // the -DRT_B200_DEV build of the library (A/B work) takes them from RT_B200_* variables
+    int shade_min = 24, slab_fast = 14, sphere_reps = 2;
+    bool hoist_media = true, prune_boxes = true, box_primitives = true, ops_in_smem = true;
+    int chunk = 32;
+    unsigned int* d_counters = nullptr;        // kLaunchSlots work counters
+    unsigned long long* d_stats = nullptr;     // kLaunchSlots x K_NUM
+    int last_slot = 0;
+    float4* d_fb = nullptr;                    // rt_render's framebuffer
     size_t fb_pixels = 0;
-    rt_render_stats last{};
+    uint8_t* d_rgb8 = nullptr;                 // rt_finalize_rgb8's output
+    size_t rgb8_bytes = 0;
+    void* h_stage[2] = {nullptr, nullptr};     // pinned staging
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    std::vector<std::pair<void*, size_t>> free_blocks;   // device blocks released by rt_scene_destroy, reused by the next upload
     uint64_t launches = 0;
+    int live_scenes = 0;
+    bool destroyed = false;                    // rt_context_destroy was called while scenes were alive: the last scene frees it
 };
 
 struct rt_scene {
     rt_context* ctx = nullptr;
-    int n_box = 0;               // OP_BOX primitives in the world program
+    int device = 0;
     DevScene dev{};
-    std::vector<void*> allocations;
+    std::vector<std::pair<void*, size_t>> allocations;
     CompiledScene compiled;
+    uint32_t ops_bytes = 0;
+    bool ops_in_global = false;
 };
+
+static void context_free(rt_context* c) {
+    cudaSetDevice(c->device);
+    cudaFree(c->d_counters);
+    cudaFree(c->d_stats);
+    cudaFree(c->d_fb);
+    cudaFree(c->d_rgb8);
+    for (auto& b : c->free_blocks) cudaFree(b.first);
+    for (void* h : c->h_stage) if (h) cudaFreeHost(h);
+    for (cudaEvent_t e : c->stage_done) if (e) cudaEventDestroy(e);
+    delete c;
+}
+
+// Device memory for scene data comes from the context's free list first: a host that uploads a scene per frame (or per
+// bench step) gets the same blocks back instead of paying cudaMalloc / cudaFree of hundreds of megabytes every time.
+static cudaError_t ctx_alloc(rt_context* c, size_t bytes, void** out) {
+    const size_t want = bytes ? (bytes + 255) / 256 * 256 : 256;
+    size_t best = c->free_blocks.size();
+    for (size_t k = 0; k < c->free_blocks.size(); ++k)
+        if (c->free_blocks[k].second >= want && c->free_blocks[k].second <= want + want / 8 &&
+            (best == c->free_blocks.size() || c->free_blocks[k].second < c->free_blocks[best].second)) best = k;
+    if (best < c->free_blocks.size()) {
+        *out = c->free_blocks[best].first;
+        c->free_blocks.erase(c->free_blocks.begin() + best);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e == cudaErrorMemoryAllocation) {      // give the cache back and retry once
+        cudaGetLastError();
+        for (auto& b : c->free_blocks) cudaFree(b.first);
+        c->free_blocks.clear();
+        e = cudaMalloc(out, want);
+    }
+    return e;
+}
+
+// Host -> device through the two pinned staging buffers (the caller's memory is pageable as far as we know).
+static cudaError_t staged_upload(rt_context* c, void* dst, const void* src, size_t bytes) {
+    const char* s = static_cast<const char*>(src);
+    char* d = static_cast<char*>(dst);
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += kStagingBytes, k ^= 1) {
+        const size_t n = std::min(kStagingBytes, bytes - off);
+        cudaError_t e = cudaEventSynchronize(c->stage_done[k]);
+        if (e != cudaSuccess) return e;
+        std::memcpy(c->h_stage[k], s + off, n);
+        e = cudaMemcpyAsync(d + off, c->h_stage[k], n, cudaMemcpyHostToDevice, 0);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(c->stage_done[k], 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 
 extern "C" {
 
 int rt_context_create(int device_id, rt_context** out) {
     if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_context_create: out is null");
+    *out = nullptr;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) return fail(RT_ERR_NO_DEVICE, std::string("rt_context_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
@@ -405,68 +302,47 @@ int rt_context_create(int device_id, rt_context** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device_id));
     rt_context* c = new rt_context;
+    struct Guard {                 // every early return below releases what was built so far
+        rt_context* c;
+        ~Guard() { if (c) context_free(c); }
+    } guard{c};
     c->device = device_id;
     c->sm_count = prop.multiProcessorCount;
     c->total_mem = prop.totalGlobalMem;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
     c->clock_khz = khz;
-    // development switches (A/B runs; the defaults are the product)
-    if (const char* e = std::getenv("RT_B200_KERNEL")) { const int v = std::atoi(e); c->variant = v == 1 ? 1 : v == 4 ? 4 : 3; }
-    if (const char* e = std::getenv("RT_B200_POOL")) c->pool_slots = std::max(1024, std::atoi(e)) / 32 * 32;
-    if (const char* e = std::getenv("RT_B200_WF_EXTEND_BLOCKS")) c->wf_extend_blocks = std::atoi(e);
-    if (const char* e = std::getenv("RT_B200_WF_SHADE_BLOCKS")) c->wf_shade_blocks = std::atoi(e);
-    if (const char* e = std::getenv("RT_B200_WF_FETCH_MIN")) c->wf_fetch_min = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_WF_SLAB_FAST")) c->wf_slab_fast = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_TIMING")) c->timing = std::atoi(e) != 0;
-    if (const char* e = std::getenv("RT_B200_SHADE_MIN")) c->shade_min = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_SLAB_FAST")) c->slab_fast = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_SLAB_REPS")) c->slab_reps = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_SPHERE_REPS")) c->sphere_reps = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_NO_BOX")) c->box_primitives = std::atoi(e) == 0;
-    if (const char* e = std::getenv("RT_B200_SLAB_EXIT")) c->slab_exit = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_SPHERE_MIN")) c->sphere_min = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_BOX_MIN")) c->box_min = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_QUAD_MIN")) c->quad_min = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RT_B200_BOX_CLASS")) c->box_class = std::atoi(e) != 0;
-    if (const char* e = std::getenv("RT_B200_NO_PRUNE")) c->prune_boxes = std::atoi(e) == 0;
-    if (const char* e = std::getenv("RT_B200_FOLD_BOX")) c->fold_box = std::atoi(e) != 0 ? 1 : 0;
-    if (const char* e = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(e) == 0;
-    if (const char* e = std::getenv("RT_B200_MIN_BLOCKS")) { const int v = std::atoi(e); c->min_blocks = v >= 8 ? 8 : v >= 2 ? v : 4; }
-    CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes()));
-    for (int mb : {2, 3, 4, 5, 6, 7, 8})
-        CU(cudaFuncSetAttribute(v3_kernel(false, mb, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
-    for (int mb : {4, 5, 6})
-        CU(cudaFuncSetAttribute(v3_kernel(false, mb, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
-    CU(cudaFuncSetAttribute(v3_kernel(true, 1, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem_bytes(kMaxPerlinShared)));
-    CU(cudaMalloc(&c->d_path_counter, sizeof(unsigned long long)));
-    CU(cudaMalloc(&c->d_slot_cursor, sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_live, 2 * kWfBatch * sizeof(unsigned int)));
-    CU(cudaMallocHost(&c->h_live, 2 * sizeof(unsigned int)));
-    CU(cudaEventCreateWithFlags(&c->wf_event[0], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->wf_event[1], cudaEventDisableTiming));
-    int bps = 0;
-    if (c->variant == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, render_kernel, kBlockThreads, perlin_smem_bytes()));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, v3_kernel(false, c->min_blocks, false), kBlockThreads, v3_smem_bytes(1)));
-    c->blocks_per_sm = bps > 0 ? bps : 1;
-    CU(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_stats, K_NUM * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_stats, 0, K_NUM * sizeof(unsigned long long)));
+#ifdef RT_B200_DEV
+    // development switches of the A/B build; the product library is compiled without them and reads no environment
+    if (const char* v = std::getenv("RT_B200_SHADE_MIN")) c->shade_min = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("RT_B200_SLAB_FAST")) c->slab_fast = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("RT_B200_SPHERE_REPS")) c->sphere_reps = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("RT_B200_NO_BOX")) c->box_primitives = std::atoi(v) == 0;
+    if (const char* v = std::getenv("RT_B200_NO_PRUNE")) c->prune_boxes = std::atoi(v) == 0;
+    if (const char* v = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(v) == 0;
+    if (const char* v = std::getenv("RT_B200_OPS_GLOBAL")) c->ops_in_smem = std::atoi(v) == 0;
+    if (const char* v = std::getenv("RT_B200_CHUNK")) c->chunk = std::max(1, std::atoi(v));
+#endif
+    for (int counting = 0; counting < 2; ++counting)
+        for (int in_smem = 0; in_smem < 2; ++in_smem)
+            CU(cudaFuncSetAttribute(mk_kernel(counting != 0, in_smem != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    CU(cudaMalloc(&c->d_counters, kLaunchSlots * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_stats, (size_t)kLaunchSlots * K_NUM * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_stats, 0, (size_t)kLaunchSlots * K_NUM * sizeof(unsigned long long)));
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaMallocHost(&c->h_stage[k], kStagingBytes));
+        CU(cudaEventCreateWithFlags(&c->stage_done[k], cudaEventDisableTiming));
+    }
+    guard.c = nullptr;
     *out = c;
     return RT_OK;
 }
 
 void rt_context_destroy(rt_context* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
-    cudaFree(c->d_counter);
-    cudaFree(c->d_stats);
-    cudaFree(c->d_fb);
-    cudaFree(c->pool.ray0); cudaFree(c->pool.ray1); cudaFree(c->pool.hit); cudaFree(c->pool.st0); cudaFree(c->pool.st1);
-    cudaFree(c->d_path_counter); cudaFree(c->d_slot_cursor); cudaFree(c->d_live); cudaFree(c->d_reserve);
-    if (c->h_live) cudaFreeHost(c->h_live);
-    for (cudaEvent_t e : c->wf_event) if (e) cudaEventDestroy(e);
-    delete c;
+    if (c->live_scenes > 0) { c->destroyed = true; return; }   // scenes still point here: the last rt_scene_destroy frees it
+    context_free(c);
 }
 
 int rt_device_info(rt_context* c, int* sm_count, int* sm_clock_khz, size_t* total_mem) {
@@ -479,37 +355,43 @@ int rt_device_info(rt_context* c, int* sm_count, int* sm_clock_khz, size_t* tota
 
 static int upload_vec(rt_scene* s, const void* src, size_t bytes, void** dst) {
     *dst = nullptr;
-    const size_t alloc = bytes ? bytes : 16;
-    CU(cudaMalloc(dst, alloc));
-    s->allocations.push_back(*dst);
-    if (bytes) CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    cudaError_t e = ctx_alloc(s->ctx, bytes, dst);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scene data)");
+    s->allocations.push_back({*dst, bytes ? (bytes + 255) / 256 * 256 : 256});
+    if (bytes) {
+        e = staged_upload(s->ctx, *dst, src, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "scene upload");
+    }
     return RT_OK;
 }
 
-// host dry runs compile with the product's defaults; RT_B200_NO_PRUNE=1 (development) shows the stream before box pruning
-static CompileOptions dry_run_options() {
+static CompileOptions compile_options(const rt_context* c, uint32_t layout_flags) {
     CompileOptions o;
-    if (const char* e = std::getenv("RT_B200_NO_PRUNE")) o.prune_boxes = std::atoi(e) == 0;
+    if (c) { o.box_primitives = c->box_primitives; o.hoist_media = c->hoist_media; o.prune_boxes = c->prune_boxes; }
+    if (layout_flags & RT_LAYOUT_NO_PRUNE) o.prune_boxes = false;
+    if (layout_flags & RT_LAYOUT_NO_BOX_PRIMITIVES) o.box_primitives = false;
+    if (layout_flags & RT_LAYOUT_NO_HOIST) o.hoist_media = false;
+#ifdef RT_B200_DEV
     if (const char* e = std::getenv("RT_B200_COST_SPHERE")) o.cost_sphere = std::atof(e);
     if (const char* e = std::getenv("RT_B200_COST_QUAD")) o.cost_quad = std::atof(e);
     if (const char* e = std::getenv("RT_B200_COST_BOX")) o.cost_box = std::atof(e);
+#endif
     return o;
 }
 
-int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
+int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) { return rt_scene_upload_ex(c, desc, 0u, out); }
+
+int rt_scene_upload_ex(rt_context* c, const rt_scene_desc* desc, uint32_t layout_flags, rt_scene** out) {
     if (!c || !desc || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: null argument");
     CU(cudaSetDevice(c->device));
     rt_scene* s = new rt_scene;
     s->ctx = c;
+    s->device = c->device;
+    c->live_scenes++;
     const char* err = nullptr;
-    CompileOptions copt = dry_run_options();
-    copt.box_primitives = c->box_primitives;
-    copt.hoist_media = c->hoist_media;
-    copt.box_class = c->box_class && c->variant == 3;
-    copt.prune_boxes = c->prune_boxes && copt.prune_boxes;
-    int rc = compile_scene(desc, copt, &s->compiled, &err);
-    if (rc < 0) { delete s; return fail(rc, err ? err : "compile_scene failed"); }
-    if (s->compiled.n_perlin > kMaxPerlinShared) { delete s; return fail(RT_ERR_UNSUPPORTED, "more than 4 NoiseTexture tables in one scene"); }
+    s->ops_in_global = (layout_flags & RT_LAYOUT_OPS_IN_GLOBAL) != 0;
+    int rc = compile_scene(desc, compile_options(c, layout_flags), &s->compiled, &err);
+    if (rc < 0) { rt_scene_destroy(s); return fail(rc, err ? err : "compile_scene failed"); }
     const CompiledScene& cs = s->compiled;
     void* p = nullptr;
 #define UP(vec, field, type)                                                                   \
@@ -523,15 +405,8 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     UP(cs.perlin_perm, perlin_perm, const uint8_t*)
     UP(cs.precise, precise, const double4*)
 #undef UP
+    s->ops_bytes = (uint32_t)(cs.ops.size() * sizeof(F4));
     s->dev.n_words = cs.n_world_words;
-    for (int i = 0; i < cs.n_world_words; ++i) {   // words of other ops can alias a header only by accident of their bits:
-        uint32_t hdr;                               // walk op by op
-        std::memcpy(&hdr, &cs.ops[i].w, 4);
-        const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
-        if (kind == OP_BOX) s->n_box++;
-        i += (kind == OP_QUAD || kind == OP_XFORM_ENTER) ? 3 : kind == OP_BOX ? 2 : kind == OP_SPHERE ? ((flags & FLAG_MOVING) ? 2 : 1)
-             : kind == OP_MEDIUM ? ((int)flags == MEDIUM_BOUNDARY_XBOX ? 4 : 2) : 1;
-    }
     s->dev.n_media = (int)cs.hoisted_media.size();
     for (int k = 0; k < s->dev.n_media; ++k) s->dev.media_op[k] = cs.hoisted_media[k];
     s->dev.n_perlin = cs.n_perlin;
@@ -549,17 +424,13 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
             const int64_t n = (int64_t)im.width * im.height;
             uint8_t* d_rgb = nullptr;
             float4* d_tex = nullptr;
-            cudaError_t e = cudaMalloc(&d_rgb, (size_t)n * 3);
-            if (e != cudaSuccess) { rt_scene_destroy(s); return cuda_fail(e, "cudaMalloc(image rgb8)"); }
-            e = cudaMalloc(&d_tex, (size_t)n * sizeof(float4));
-            if (e != cudaSuccess) { cudaFree(d_rgb); rt_scene_destroy(s); return cuda_fail(e, "cudaMalloc(image texels)"); }
-            s->allocations.push_back(d_tex);
-            e = cudaMemcpy(d_rgb, im.rgb8, (size_t)n * 3, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) {
-                expand_image_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_rgb, n, d_lut, d_tex);
-                e = cudaDeviceSynchronize();
-            }
-            cudaFree(d_rgb);
+            rc = upload_vec(s, im.rgb8, (size_t)n * 3, (void**)&d_rgb);      // returns to the context's free list with the scene
+            if (rc < 0) { rt_scene_destroy(s); return rc; }
+            cudaError_t e = ctx_alloc(c, (size_t)n * sizeof(float4), (void**)&d_tex);
+            if (e != cudaSuccess) { rt_scene_destroy(s); return cuda_fail(e, "cudaMalloc(image texels)"); }
+            s->allocations.push_back({d_tex, ((size_t)n * sizeof(float4) + 255) / 256 * 256});
+            expand_image_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_rgb, n, d_lut, d_tex);
+            e = cudaGetLastError();
             if (e != cudaSuccess) { rt_scene_destroy(s); return cuda_fail(e, "image upload"); }
             imgs[k].texels = d_tex;
             imgs[k].width = im.width;
@@ -569,56 +440,58 @@ int rt_scene_upload(rt_context* c, const rt_scene_desc* desc, rt_scene** out) {
     rc = upload_vec(s, imgs.data(), imgs.size() * sizeof(DevImage), &p);
     if (rc < 0) { rt_scene_destroy(s); return rc; }
     s->dev.images = static_cast<const DevImage*>(p);
+    cudaError_t e = cudaDeviceSynchronize();    // the caller may free its host arrays when this returns
+    if (e != cudaSuccess) { rt_scene_destroy(s); return cuda_fail(e, "rt_scene_upload"); }
     *out = s;
     return RT_OK;
 }
 
-int rt_scene_layout(const rt_scene_desc* desc, rt_layout_info* out) {
+int rt_scene_layout(const rt_scene_desc* desc, uint32_t layout_flags, rt_layout_info* out) {
     if (!desc || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_layout: null argument");
     CompiledScene cs;
     const char* err = nullptr;
-    const int rc = compile_scene(desc, dry_run_options(), &cs, &err);
+    const int rc = compile_scene(desc, compile_options(nullptr, layout_flags), &cs, &err);
     if (rc < 0) return fail(rc, err ? err : "compile_scene failed");
     std::memset(out, 0, sizeof(*out));
     out->n_words = cs.n_world_words;
-    const int n_all = (int)cs.ops.size() - 2;   // without the two padding words
-    for (int i = 0; i < cs.n_world_words;) {
+    for (int i = 0; i < cs.n_world_words;) {   // words of other ops can alias a header only by accident of their bits: walk op by op
         uint32_t hdr;
         std::memcpy(&hdr, &cs.ops[i].w, 4);
-        const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
+        const uint32_t kind = hdr_kind(hdr), flags = hdr_flags(hdr);
         switch (kind) {
-            case OP_INNER: case OP_INNER_REF: out->n_inner++; i += 2; break;
-            case OP_SPHERE: out->n_sphere++; i += (flags & FLAG_MOVING) ? 3 : 2; break;
-            case OP_QUAD: out->n_quad++; i += 4; break;
-            case OP_XFORM_ENTER: out->n_xform++; i += 4; break;
-            case OP_XFORM_EXIT: i += 2; break;
-            case OP_MEDIUM: out->n_medium_in_stream++; i += (int)flags == MEDIUM_BOUNDARY_XBOX ? 5 : 3; break;
-            case OP_BOX: out->n_box++; i += 3; break;
+            case OP_INNER: case OP_INNER_REF: out->n_inner++; break;
+            case OP_SPHERE: out->n_sphere++; break;
+            case OP_QUAD: out->n_quad++; break;
+            case OP_XFORM_ENTER: out->n_xform++; break;
+            case OP_XFORM_EXIT: break;
+            case OP_MEDIUM: out->n_medium_in_stream++; break;
+            case OP_BOX: out->n_box++; break;
             default: return fail(RT_ERR_INTERNAL, "rt_scene_layout: bad op in stream");
         }
+        i += op_words(kind, flags);
     }
     out->n_medium_hoisted = (int32_t)cs.hoisted_media.size();
     out->n_precise_spheres = (int32_t)cs.precise.size() / 2;
     out->n_bvh = (int32_t)cs.bvh_hittable_ids.size();
-    int64_t bytes = (int64_t)(n_all + 2) * 16 + (int64_t)(cs.materials.size() + cs.textures.size() + cs.perlin_vec.size()) * 16 +
+    int64_t bytes = (int64_t)cs.ops.size() * 16 + (int64_t)(cs.materials.size() + cs.textures.size() + cs.perlin_vec.size()) * 16 +
                     (int64_t)cs.perlin_perm.size() + (int64_t)cs.precise.size() * 32;
     for (int k = 0; k < desc->n_images; ++k) bytes += (int64_t)desc->images[k].width * desc->images[k].height * 16;
     out->device_bytes = bytes;
     return RT_OK;
 }
 
-int rt_scene_ops_export(const rt_scene_desc* desc, float* words, int64_t capacity_words, int64_t* n_total_words,
-                        int32_t* n_world_words, int32_t* media_ops, int32_t* n_media, int32_t* first_class) {
+int rt_scene_ops_export(const rt_scene_desc* desc, uint32_t layout_flags, float* words, int64_t capacity_words, int64_t* n_total_words,
+                        int32_t* n_world_words, int32_t* media_ops, int32_t* n_media, uint32_t* first_link) {
     if (!desc || !n_total_words) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_ops_export: null argument");
     CompiledScene cs;
     const char* err = nullptr;
-    const int rc = compile_scene(desc, dry_run_options(), &cs, &err);
+    const int rc = compile_scene(desc, compile_options(nullptr, layout_flags), &cs, &err);
     if (rc < 0) return fail(rc, err ? err : "compile_scene failed");
     *n_total_words = (int64_t)cs.ops.size();
     if (n_world_words) *n_world_words = cs.n_world_words;
     if (n_media) *n_media = (int32_t)cs.hoisted_media.size();
     if (media_ops) for (size_t k = 0; k < cs.hoisted_media.size() && k < (size_t)kMaxHoistedMedia; ++k) media_ops[k] = cs.hoisted_media[k];
-    if (first_class) *first_class = (int32_t)cs.first_class;
+    if (first_link) *first_link = cs.first_link;
     if (words) {
         if (capacity_words < (int64_t)cs.ops.size()) return fail(RT_ERR_OUT_OF_RANGE, "rt_scene_ops_export: capacity too small");
         std::memcpy(words, cs.ops.data(), cs.ops.size() * sizeof(F4));
@@ -628,139 +501,26 @@ int rt_scene_ops_export(const rt_scene_desc* desc, float* words, int64_t capacit
 
 void rt_scene_destroy(rt_scene* s) {
     if (!s) return;
-    if (s->ctx) cudaSetDevice(s->ctx->device);
-    for (void* p : s->allocations) cudaFree(p);
+    cudaSetDevice(s->device);
+    rt_context* c = s->ctx;
+    if (c) {
+        cudaDeviceSynchronize();                  // nothing in flight may still read these blocks when they are handed out again
+        size_t cached = 0;
+        for (auto& b : c->free_blocks) cached += b.second;
+        for (auto& b : s->allocations) {
+            if (!c->destroyed && cached + b.second <= (size_t)2 << 30) { c->free_blocks.push_back(b); cached += b.second; }
+            else cudaFree(b.first);
+        }
+        c->live_scenes--;
+        if (c->destroyed && c->live_scenes == 0) context_free(c);
+    } else {
+        for (auto& b : s->allocations) cudaFree(b.first);
+    }
     delete s;
-}
-
-// Wavefront render (render_v4.cuh): alternate wf_shade_kernel / wf_extend_kernel over the pool until no slot carries
-// a ray. Iterations are enqueued in batches of kWfBatch; the live flag of batch b is looked at after batch b + 1 has
-// been enqueued, so the stream never runs dry while the host decides. Returns with the stream drained.
-static size_t wf_shade_smem(int n_perlin) {
-    const int np = n_perlin < kMaxPerlinShared ? n_perlin : kMaxPerlinShared;
-    return (size_t)np * (256 * sizeof(float4) + 768);
-}
-
-static int wf_ensure_pool(rt_context* c, size_t slots) {
-    if (c->pool_capacity >= slots) return RT_OK;
-    cudaFree(c->pool.ray0); cudaFree(c->pool.ray1); cudaFree(c->pool.hit); cudaFree(c->pool.st0); cudaFree(c->pool.st1);
-    c->pool = WavePool{};
-    c->pool_capacity = 0;
-    CU(cudaMalloc(&c->pool.ray0, slots * sizeof(float4)));
-    CU(cudaMalloc(&c->pool.ray1, slots * sizeof(float4)));
-    CU(cudaMalloc(&c->pool.hit, slots * sizeof(float4)));
-    CU(cudaMalloc(&c->pool.st0, slots * sizeof(float4)));
-    CU(cudaMalloc(&c->pool.st1, slots * sizeof(float4)));
-    c->pool_capacity = slots;
-    return RT_OK;
-}
-
-static int launch_render_v4(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
-                            int64_t sample_count, uint64_t seed, void* d_sum_rgba, cudaStream_t stream) {
-    WfParams prm;
-    prm.scene = s->dev;
-    prm.cam = make_dev_camera(*cam);
-    prm.seed = seed;
-    prm.sample_begin = sample_begin;
-    prm.n_pixels = (uint32_t)((int64_t)prm.cam.width * prm.cam.height);
-    prm.n_paths = (unsigned long long)prm.n_pixels * (unsigned long long)sample_count;
-    prm.tiled = (prm.cam.width % kTileW == 0 && prm.cam.height % kTileH == 0) ? 1 : 0;
-    prm.tiles_x = prm.cam.width / kTileW;
-    size_t slots = (size_t)c->pool_slots;
-    const unsigned long long rounded = (prm.n_paths + 31ull) / 32ull * 32ull;
-    if (rounded < (unsigned long long)slots) slots = (size_t)rounded;
-    int rc = wf_ensure_pool(c, slots);
-    if (rc < 0) return rc;
-    prm.pool = c->pool;
-    prm.pool.n_slots = (int)slots;
-    prm.sum = static_cast<float4*>(d_sum_rgba);
-    prm.path_counter = c->d_path_counter;
-    prm.slot_cursor = c->d_slot_cursor;
-    prm.stats = c->d_stats;
-    prm.first_class = (int)s->compiled.first_class;
-    prm.fetch_min = c->wf_fetch_min;
-    prm.slab_fast = c->wf_slab_fast;
-    prm.sphere_reps = c->sphere_reps;
-    prm.slab_exit = c->slab_exit;
-    prm.sphere_min = c->sphere_min;
-
-    wf_extend_fn extend = wf_extend(c->wf_extend_blocks);
-    wf_shade_fn shade_k = wf_shade(c->wf_shade_blocks);
-    const size_t smem = wf_shade_smem(s->dev.n_perlin);
-    int bps_e = 1, bps_s = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_e, extend, kBlockThreads, 0));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_s, shade_k, kWfShadeThreads, smem));
-    const size_t slot_warps = slots / 32;
-    size_t grid_e = (size_t)c->sm_count * (size_t)std::max(1, bps_e);
-    size_t grid_s = (size_t)c->sm_count * (size_t)std::max(1, bps_s);
-    grid_e = std::max<size_t>(1, std::min(grid_e, (slot_warps + kBlockThreads / 32 - 1) / (kBlockThreads / 32)));
-    grid_s = std::max<size_t>(1, std::min(grid_s, (slot_warps + kWfShadeThreads / 32 - 1) / (kWfShadeThreads / 32)));
-    const size_t shade_warps = grid_s * (kWfShadeThreads / 32);
-    if (c->reserve_warps < shade_warps) {
-        cudaFree(c->d_reserve);
-        c->d_reserve = nullptr;
-        c->reserve_warps = 0;
-        CU(cudaMalloc(&c->d_reserve, shade_warps * sizeof(ulonglong2)));
-        c->reserve_warps = shade_warps;
-    }
-    prm.reserve = c->d_reserve;
-
-    CU(cudaMemsetAsync(c->d_path_counter, 0, sizeof(unsigned long long), stream));
-    CU(cudaMemsetAsync(c->d_slot_cursor, 0, sizeof(unsigned int), stream));
-    CU(cudaMemsetAsync(c->d_reserve, 0, shade_warps * sizeof(ulonglong2), stream));
-    CU(cudaMemsetAsync(c->d_stats, 0, K_NUM * sizeof(unsigned long long), stream));
-    wf_init_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(prm.pool.hit, (int)slots);
-    c->launches += 1;
-    c->ms_extend = c->ms_shade = 0.0;
-    c->wf_iterations = 0;
-
-    struct EventBag {               // timing mode: begin / middle / end of every iteration; destroyed on every exit path
-        std::vector<cudaEvent_t> v;
-        ~EventBag() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
-    } bag;
-    std::vector<cudaEvent_t>& tev = bag.v;
-    for (int b = 0;; ++b) {
-        unsigned int* live = c->d_live + (b & 1) * kWfBatch;
-        prm.live_flag = live;
-        CU(cudaMemsetAsync(live, 0, kWfBatch * sizeof(unsigned int), stream));
-        for (int k = 0; k < kWfBatch; ++k) {
-            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-            if (c->timing) {
-                cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-                tev.push_back(e0); tev.push_back(e1); tev.push_back(e2);
-                cudaEventRecord(e0, stream);
-            }
-            shade_k<<<(unsigned)grid_s, kWfShadeThreads, smem, stream>>>(prm, k);
-            if (c->timing) cudaEventRecord(e1, stream);
-            extend<<<(unsigned)grid_e, kBlockThreads, 0, stream>>>(prm);
-            if (c->timing) cudaEventRecord(e2, stream);
-        }
-        CU(cudaGetLastError());
-        c->launches += 2 * kWfBatch;
-        c->wf_iterations += kWfBatch;
-        CU(cudaMemcpyAsync(c->h_live + (b & 1), live + (kWfBatch - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-        CU(cudaEventRecord(c->wf_event[b & 1], stream));
-        if (b >= 1) {
-            CU(cudaEventSynchronize(c->wf_event[(b - 1) & 1]));
-            if (c->h_live[(b - 1) & 1] == 0u) break;
-        }
-    }
-    CU(cudaStreamSynchronize(stream));
-    if (c->timing) {
-        for (size_t k = 0; k + 2 < tev.size(); k += 3) {
-            float a = 0.0f, b2 = 0.0f;
-            cudaEventElapsedTime(&a, tev[k], tev[k + 1]);
-            cudaEventElapsedTime(&b2, tev[k + 1], tev[k + 2]);
-            c->ms_shade += a;
-            c->ms_extend += b2;
-        }
-    }
-    return RT_OK;
 }
 
 static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
                          int64_t sample_count, uint64_t seed, void* d_sum_rgba, cudaStream_t stream, bool counting) {
-    if (c->variant == 4 && !counting) return launch_render_v4(c, s, cam, sample_begin, sample_count, seed, d_sum_rgba, stream);
     RenderParams prm;
     prm.scene = s->dev;
     prm.cam = make_dev_camera(*cam);
@@ -772,48 +532,44 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     // pool = tile x chunk samples; keep >= 64 pools per resident warp so the tail of the launch (warps running dry
     // while others still hold a pool) stays near 1%: short renders get small chunks, the 10000-spp bench keeps 32
     const int64_t n_tiles = (int64_t)prm.tiles_x * prm.tiles_y;
-    const int64_t resident_warps = (int64_t)c->sm_count * c->blocks_per_sm * (kBlockThreads / 32);
-    int chunk = 32;
-    if (const char* e = std::getenv("RT_B200_CHUNK")) chunk = std::max(1, std::atoi(e));
+    const int64_t resident_warps = (int64_t)c->sm_count * (kRenderThreads / 32);
+    int chunk = c->chunk;
     while (chunk > 1 && n_tiles * ((sample_count + chunk - 1) / chunk) < resident_warps * 64) chunk >>= 1;
     prm.chunk = chunk;
     prm.n_chunks = (int)((sample_count + chunk - 1) / chunk);
     if ((uint64_t)n_tiles * (uint64_t)prm.n_chunks >= 0xffffffffull) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: too many work items; split the sample range");
     prm.sum = static_cast<float4*>(d_sum_rgba);
-    prm.work_counter = c->d_counter;
-    prm.stats = c->d_stats;
-    prm.first_class = (int)s->compiled.first_class;
+    const int slot = (int)(c->launches % kLaunchSlots);
+    prm.work_counter = c->d_counters + slot;
+    prm.stats = c->d_stats + (size_t)slot * K_NUM;
+    prm.first_link = s->compiled.first_link;
     prm.shade_min = c->shade_min;
     prm.slab_fast = c->slab_fast;
-    prm.slab_reps = c->slab_reps;
     prm.sphere_reps = c->sphere_reps;
-    prm.slab_exit = c->slab_exit;
-    prm.sphere_min = c->sphere_min;
-    prm.box_min = c->box_min;
-    prm.quad_min = c->quad_min;
-    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), stream));
-    CU(cudaMemsetAsync(c->d_stats, 0, K_NUM * sizeof(unsigned long long), stream));
-    int grid = c->sm_count * c->blocks_per_sm;
-    if (counting || c->variant == 3) {
-        const size_t smem = v3_smem_bytes(s->dev.n_perlin);
-        const bool fold = c->fold_box < 0 ? s->n_box >= kFoldBoxMin : c->fold_box != 0;
-        render_fn fn = v3_kernel(counting, c->min_blocks, fold);
-        int bps = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, kBlockThreads, smem));
-        grid = c->sm_count * (bps > 0 ? bps : 1);
-        fn<<<grid, kBlockThreads, smem, stream>>>(prm);
-    } else {
-        render_kernel<<<grid, kBlockThreads, perlin_smem_bytes(), stream>>>(prm);
-    }
+    // the op stream rides in shared memory when it fits beside the per-thread path state and the Perlin tables
+    MkSmem lay = mk_smem_layout(s->ops_bytes, s->dev.n_perlin);
+    const bool in_smem = c->ops_in_smem && !s->ops_in_global && lay.total <= c->smem_optin;
+    if (!in_smem) lay = mk_smem_layout(0, s->dev.n_perlin);
+    if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: per-thread state does not fit in shared memory");
+    prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
+    CU(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned int), stream));
+    CU(cudaMemsetAsync(prm.stats, 0, K_NUM * sizeof(unsigned long long), stream));
+    render_fn fn = mk_kernel(counting, in_smem);
+    fn<<<c->sm_count, kRenderThreads, lay.total, stream>>>(prm);
     CU(cudaGetLastError());
+    c->last_slot = slot;
     c->launches += 1;
     return RT_OK;
 }
 
-static int check_render_args(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_count, const void* buf,
-                             const char* who) {
+static int check_render_args(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin, int64_t sample_count,
+                             const void* buf, const char* who) {
     if (!c || !s || !cam || !buf) return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": null argument");
+    if (s->ctx != c) return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": the scene was uploaded through another context");
     if (sample_count < 0 || sample_count > 0x7fffffff) return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": bad sample_count");
+    // the RNG key takes the sample index as 32 bits (path_key): a range past 2^32 would silently reuse keys
+    if (sample_begin < 0 || sample_begin + sample_count > (int64_t)1 << 32)
+        return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": sample range must lie in [0, 2^32)");
     if (cam->image_width <= 0 || cam->image_height <= 0 || cam->image_width * cam->image_height > 0x7fffffff)
         return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": bad image size");
     if (cam->max_depth <= 0)   // ray_color returns black at depth <= 0 (renderer.rs:140-142); the CLI scenes never ask for it
@@ -823,8 +579,10 @@ static int check_render_args(rt_context* c, const rt_scene* s, const rt_camera_d
 
 int rt_render_accumulate(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
                          int64_t sample_count, uint64_t seed, void* d_sum_rgba, void* stream_) {
-    int rc = check_render_args(c, s, cam, sample_count, d_sum_rgba, "rt_render_accumulate");
+    int rc = check_render_args(c, s, cam, sample_begin, sample_count, d_sum_rgba, "rt_render_accumulate");
     if (rc < 0) return rc;
+    if ((reinterpret_cast<uintptr_t>(d_sum_rgba) & 15u) != 0)   // red.global.add.v4.f32
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: the framebuffer must be 16-byte aligned");
     if (sample_count == 0) return RT_OK;
     CU(cudaSetDevice(c->device));
     return launch_render(c, s, cam, sample_begin, sample_count, seed, d_sum_rgba, static_cast<cudaStream_t>(stream_), false);
@@ -832,7 +590,7 @@ int rt_render_accumulate(rt_context* c, const rt_scene* s, const rt_camera_desc*
 
 int rt_render_count_ops(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin, int64_t sample_count,
                         uint64_t seed, uint64_t* counters, int capacity, const char** names_csv) {
-    int rc = check_render_args(c, s, cam, sample_count, counters, "rt_render_count_ops");
+    int rc = check_render_args(c, s, cam, sample_begin, sample_count, counters, "rt_render_count_ops");
     if (rc < 0) return rc;
     if (capacity < (int)K_NUM) return fail(RT_ERR_OUT_OF_RANGE, "rt_render_count_ops: capacity too small");
     if (names_csv) *names_csv = kCounterNames;
@@ -841,9 +599,12 @@ int rt_render_count_ops(rt_context* c, const rt_scene* s, const rt_camera_desc* 
     float4* scratch = nullptr;
     CU(cudaMalloc(&scratch, n * sizeof(float4)));
     cudaMemset(scratch, 0, n * sizeof(float4));
-    rc = sample_count > 0 ? launch_render(c, s, cam, sample_begin, sample_count, seed, scratch, nullptr, true) : RT_OK;
     unsigned long long h[K_NUM] = {0};
-    cudaError_t e = cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaSuccess;
+    if (sample_count > 0) {
+        rc = launch_render(c, s, cam, sample_begin, sample_count, seed, scratch, nullptr, true);
+        if (rc == RT_OK) e = cudaMemcpy(h, c->d_stats + (size_t)c->last_slot * K_NUM, sizeof(h), cudaMemcpyDeviceToHost);
+    }
     cudaFree(scratch);
     if (rc < 0) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "rt_render_count_ops");
@@ -854,8 +615,9 @@ int rt_render_count_ops(rt_context* c, const rt_scene* s, const rt_camera_desc* 
 int rt_render_get_stats(rt_context* c, rt_render_stats* out) {
     if (!c || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_get_stats: null argument");
     CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());    // the last launch may sit on a non-blocking stream: wait for the whole device
     unsigned long long h[2] = {0, 0};
-    CU(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h, c->d_stats + (size_t)c->last_slot * K_NUM, sizeof(h), cudaMemcpyDeviceToHost));
     out->paths = h[0];
     out->segments = h[1];
     out->kernel_launches = c->launches;
@@ -863,18 +625,10 @@ int rt_render_get_stats(rt_context* c, rt_render_stats* out) {
     return RT_OK;
 }
 
-int rt_render_get_kernel_times(rt_context* c, double* ms_shade, double* ms_extend, uint64_t* iterations) {
-    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_get_kernel_times: context is null");
-    if (ms_shade) *ms_shade = c->ms_shade;
-    if (ms_extend) *ms_extend = c->ms_extend;
-    if (iterations) *iterations = c->wf_iterations;
-    return RT_OK;
-}
-
-int rt_render(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin, int64_t sample_count,
-              uint64_t seed, float* host_sum_rgba) {
-    if (!c || !s || !cam || !host_sum_rgba) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: null argument");
-    if (cam->image_width <= 0 || cam->image_height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: bad image size");
+static int render_into_context_fb(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin,
+                                  int64_t sample_count, uint64_t seed, const char* who) {
+    if (!c || !s || !cam) return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": null argument");
+    if (cam->image_width <= 0 || cam->image_height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": bad image size");
     CU(cudaSetDevice(c->device));
     const size_t n = (size_t)cam->image_width * (size_t)cam->image_height;
     if (c->fb_pixels < n) {
@@ -885,23 +639,45 @@ int rt_render(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64
         c->fb_pixels = n;
     }
     CU(cudaMemsetAsync(c->d_fb, 0, n * sizeof(float4), 0));
-    int rc = rt_render_accumulate(c, s, cam, sample_begin, sample_count, seed, c->d_fb, nullptr);
+    return rt_render_accumulate(c, s, cam, sample_begin, sample_count, seed, c->d_fb, nullptr);
+}
+
+int rt_render(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin, int64_t sample_count,
+              uint64_t seed, float* host_sum_rgba) {
+    if (!host_sum_rgba) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: null argument");
+    const int rc = render_into_context_fb(c, s, cam, sample_begin, sample_count, seed, "rt_render");
     if (rc < 0) return rc;
-    CU(cudaMemcpy(host_sum_rgba, c->d_fb, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host_sum_rgba, c->d_fb, (size_t)cam->image_width * (size_t)cam->image_height * sizeof(float4), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 
-int rt_finalize_rgb8(rt_context* c, const void* d_sum_rgba, int64_t n_pixels, double spp, uint8_t* host_rgb8) {
+int rt_render_rgb8(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, int64_t sample_begin, int64_t sample_count,
+                   uint64_t seed, uint8_t* host_rgb8) {
+    if (!host_rgb8) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_rgb8: null argument");
+    const int rc = render_into_context_fb(c, s, cam, sample_begin, sample_count, seed, "rt_render_rgb8");
+    if (rc < 0) return rc;
+    return rt_finalize_rgb8(c, c->d_fb, cam->image_width * cam->image_height, (double)sample_count, host_rgb8, nullptr);
+}
+
+int rt_finalize_rgb8(rt_context* c, const void* d_sum_rgba, int64_t n_pixels, double spp, uint8_t* host_rgb8, void* stream_) {
     if (!c || !d_sum_rgba || !host_rgb8) return fail(RT_ERR_INVALID_ARGUMENT, "rt_finalize_rgb8: null argument");
     if (n_pixels <= 0) return RT_OK;
     CU(cudaSetDevice(c->device));
-    uint8_t* d_rgb = nullptr;
-    CU(cudaMalloc(&d_rgb, (size_t)n_pixels * 3));
-    finalize_kernel<<<(unsigned)((n_pixels + 255) / 256), 256>>>(static_cast<const float4*>(d_sum_rgba), n_pixels,
-                                                               spp > 0 ? (float)(1.0 / spp) : 0.0f, spp > 0 ? 0 : 1, d_rgb);
-    cudaError_t e = cudaMemcpy(host_rgb8, d_rgb, (size_t)n_pixels * 3, cudaMemcpyDeviceToHost);
-    cudaFree(d_rgb);
-    if (e != cudaSuccess) return cuda_fail(e, "rt_finalize_rgb8");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t bytes = (size_t)n_pixels * 3;
+    if (c->rgb8_bytes < bytes) {
+        cudaFree(c->d_rgb8);
+        c->d_rgb8 = nullptr;
+        c->rgb8_bytes = 0;
+        CU(cudaMalloc(&c->d_rgb8, bytes));
+        c->rgb8_bytes = bytes;
+    }
+    // on the caller's stream: ordered after the rt_render_accumulate calls that filled the framebuffer there
+    finalize_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, stream>>>(static_cast<const float4*>(d_sum_rgba), n_pixels,
+                                                                          spp > 0 ? (float)(1.0 / spp) : 0.0f, spp > 0 ? 0 : 1, c->d_rgb8);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_rgb8, c->d_rgb8, bytes, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
     return RT_OK;
 }
 

@@ -1,10 +1,12 @@
 // Device code of the ray_color hot path (renderer.rs:26-49,139-155 and everything it calls),
 // written for sm_100a. f32 arithmetic except where a primitive is flagged FLAG_PRECISE.
 //
-//   traverse<>()      world.hit(ray, ray_t): BVHNode / HittableList / Translate / RotateY /
-//                     Sphere / Quad / ConstantMedium (bvh.rs:90-113, hittable.rs:61-188,
-//                     sphere.rs:59-89, quad.rs:97-133, constant_medium.rs:34-70) as one stackless
-//                     loop over the threaded op stream (dev_scene.h)
+//   sphere_test / quad_test / box_accept / medium_test / slab_ch
+//                     Sphere / Quad / Quad::cube / ConstantMedium / AABB (sphere.rs:59-89, quad.rs:97-133,
+//                     constant_medium.rs:34-70, aabb.rs:64-84), shared by every kernel
+//   traverse<>()      world.hit(ray, ray_t) as one stackless loop over the threaded op stream (dev_scene.h;
+//                     bvh.rs:90-113, hittable.rs:61-188) - the parity kernels' form; the render kernel (render_mk.cuh)
+//                     walks the same stream with the same tests, regrouping its lanes by op class
 //   finalize_hit()    HitRecord::new + uv (hittable.rs:22-37, sphere.rs:48-52) for the winner only
 //   texture_value()   texture.rs:32-111 + perlin.rs:27-100 (tables in shared memory)
 //   shade()           Material::emitted / scatter (material.rs:26-138)
@@ -103,24 +105,68 @@ struct Best {
     int xf;   // word index of the enclosing OP_XFORM_ENTER, -1 = world space
 };
 
-// Per-lane traversal cursor over the threaded op stream.
-struct Trav {
-    float3 o, d, inv;   // current (possibly instance-local) ray and its reciprocal direction
-    float3 so, sd;      // the world ray: every OP_XFORM_ENTER holds the composed world -> local transform, nested or not
-    int cur_xf;         // word index of the active OP_XFORM_ENTER, -1 = none
-    int i;              // word index of the next op
-    Best best;
+// Where the op stream is read from. Offsets are BYTE offsets (the low 28 bits of a link, dev_scene.h).
+struct OpsGlobal {   // parity kernels, and render launches whose stream does not fit in shared memory
+    const float4* base;
+    __device__ __forceinline__ float4 operator()(uint32_t byte_off) const {
+        return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(base) + byte_off));
+    }
+};
+// The render kernel: the whole stream staged in shared memory by one bulk (TMA) copy per CTA, kSmemOps bytes into the
+// dynamic shared window (render_mk.cuh: [0, 8) the copy's mbarrier, [16, 528) the launch parameters). Addressed off the
+// symbol so a fetch is one LDS.128 with an immediate offset.
+extern __shared__ float4 dyn_smem[];
+constexpr uint32_t kSmemParams = 16;
+constexpr uint32_t kSmemOps = 16 + 512;
+struct OpsShared {
+    __device__ __forceinline__ float4 operator()(uint32_t byte_off) const {
+        return *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(dyn_smem) + kSmemOps + byte_off);
+    }
 };
 
-// origin code of a ray that starts on a surface: (op word index << 3) | box face; -1 = none.
-__device__ __forceinline__ int origin_code(int op, int face) { return (op << 3) | face; }
-
+// Per-ray constants of the centre / half-extent slab test (dev_scene.h, CULL BOXES).
+struct RaySetup {
+    float3 inv, oi;         // 1/d, -o/d
+    float eps;              // 2^-21 max_k |o_k / d_k| over the axes with a finite quotient
+    float a, inv_a;         // |d|^2 and its reciprocal (sphere tests)
+};
 __device__ __forceinline__ float3 safe_inv(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+__device__ __forceinline__ RaySetup ray_setup(float3 o, float3 d) {
+    RaySetup R;
+    R.inv = safe_inv(d);
+    R.oi = f3(-o.x * R.inv.x, -o.y * R.inv.y, -o.z * R.inv.z);
+    const float inf = __int_as_float(0x7f800000);
+    const float ex = fabsf(R.oi.x), ey = fabsf(R.oi.y), ez = fabsf(R.oi.z);   // NaN (0 * inf) and inf axes constrain nothing
+    R.eps = 4.76837158e-7f * fmaxf(fmaxf(ex < inf ? ex : 0.0f, ey < inf ? ey : 0.0f), ez < inf ? ez : 0.0f);
+    R.a = dot(d, d);
+    R.inv_a = 1.0f / R.a;
+    return R;
+}
 
-// Entry / exit parameters of the ray against the box {w0.xyz, w1.xyz}, not clamped to any interval.
-// Near/far planes are chosen by the sign of the reciprocal direction (as aabb.rs:73-75 swaps on inv_d < 0), and
-// fminf/fmaxf drop a NaN operand like f64::min/max do: a 0*inf product (origin exactly on a slab plane of a ray
-// parallel to it) leaves that axis unconstrained, which is what the reference computes.
+// origin code of a ray that starts on a surface: (byte offset of the op) | box face; -1 = none. Byte offsets are
+// multiples of 16, so the face lives in the low nibble and "does this ray start on the op at `link`" is one masked xor.
+__device__ __forceinline__ int origin_code(int op_word, int face) { return (op_word << 4) | face; }
+__device__ __forceinline__ bool starts_on(int origin, uint32_t link) { return (((uint32_t)origin ^ link) & 0x0ffffff0u) == 0u; }
+
+// Entry / exit parameters of the ray against the cull box {c = w0.xyz, h = w1.xyz}, not clamped to any interval.
+// fminf/fmaxf drop a NaN operand like f64::min/max do (aabb.rs:76-77): an axis the ray is parallel to (inv = inf,
+// tc = inf - inf) constrains nothing here - the classic form would still test the origin against that slab; boxes only
+// cull, so passing a few more is allowed.
+__device__ __forceinline__ void slab_ch(float4 w0, float4 w1, const float3& inv, const float3& oi, float* t_enter, float* t_exit) {
+    const float tcx = fmaf(w0.x, inv.x, oi.x), tcy = fmaf(w0.y, inv.y, oi.y), tcz = fmaf(w0.z, inv.z, oi.z);
+    const float thx = fabsf(w1.x * inv.x), thy = fabsf(w1.y * inv.y), thz = fabsf(w1.z * inv.z);   // |.| is an operand modifier
+    *t_enter = fmaxf(fmaxf(tcx - thx, tcy - thy), tcz - thz);
+    *t_exit = fminf(fminf(tcx + thx, tcy + thy), tcz + thz);
+}
+// AABB::hit (aabb.rs:64-84) for a padded cull box: tight slab test with the reciprocal hoisted per ray (permitted
+// substitution, SURVEY.md §8(a)-Q: it only culls more, it never changes which hits exist).
+constexpr float kSlabSlack = 1.0000012f;
+__device__ __forceinline__ bool cull_pass(float te, float tx, float tmin, float tmax, float eps) {
+    return fmaxf(te, tmin) <= fmaf(fminf(tx, tmax), kSlabSlack, eps);
+}
+
+// Entry / exit against exact corners {lo = w0.xyz, hi = w1.xyz} in the classic form (no cancellation): box primitives
+// whose ray starts on one of their faces, medium boundaries, hit records.
 __device__ __forceinline__ void slab_interval(float4 w0, float4 w1, float3 o, float3 inv, float* t_enter, float* t_exit) {
     const float ax = (w0.x - o.x) * inv.x, bx = (w1.x - o.x) * inv.x;
     const float ay = (w0.y - o.y) * inv.y, by = (w1.y - o.y) * inv.y;
@@ -128,17 +174,6 @@ __device__ __forceinline__ void slab_interval(float4 w0, float4 w1, float3 o, fl
     const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
     *t_enter = fmaxf(fmaxf(sx ? bx : ax, sy ? by : ay), sz ? bz : az);
     *t_exit = fminf(fminf(sx ? ax : bx, sy ? ay : by), sz ? az : bz);
-}
-
-// AABB::hit (aabb.rs:64-84) as a tight slab test with the reciprocal hoisted per ray (permitted
-// substitution, SURVEY.md §8(a)-Q: it only culls more, it never changes which hits exist). The exit
-// side is inflated by a few ulp so f32 rounding can never cull a box the ray grazes.
-__device__ __forceinline__ bool slab(float4 w0, float4 w1, float3 o, float3 inv, float tmin, float tmax) {
-    float te, tx;
-    slab_interval(w0, w1, o, inv, &te, &tx);
-    te = fmaxf(te, tmin);
-    tx = fminf(tx, tmax);
-    return te <= tx * 1.0000012f + 1e-30f || te <= tx;
 }
 
 // AABB::hit exactly as aabb.rs:64-84 states it: every axis is tested against the ORIGINAL interval, the interval is
@@ -157,11 +192,8 @@ __device__ __forceinline__ bool aabb_hit_reference(float4 w0, float4 w1, float3 
 
 // local = R(x - a) + b with R = rotate-y as in hittable.rs:164-168.
 // Written with explicit round-to-nearest intrinsics, which the compiler never contracts or re-associates: the traversal
-// (entering an instance) and finalize_hit() (recomputing the local ray of the winner) must produce the SAME bits, because
-// a cube's face is recognised by t == plane parameter exactly. With plain operators the two inline sites could get
-// different FMA contractions: a 1-ulp difference then mis-identifies the face, the self-intersection guard of the next
-// segment looks at the wrong plane, and the path re-hits its own surface until max_depth (seen once the instance code
-// was restructured: a handful of 90 000 Cornell paths trapped; the wavefront kernel, compiled separately, was unaffected).
+// (entering an instance) and finalize_hit() (recomputing the local ray of the winner) then produce the SAME bits, so a
+// plane parameter computed at the two sites cannot differ by a contraction.
 __device__ __forceinline__ float3 xform_point(float3 x, float4 w2, float4 w3) {
     const float qx = __fsub_rn(x.x, w2.x), qy = __fsub_rn(x.y, w2.y), qz = __fsub_rn(x.z, w2.z);
     const float s = w2.w, c = w3.w;
@@ -181,10 +213,10 @@ __device__ __forceinline__ float3 xform_dir_back(float3 v, float4 w2, float4 w3)
 // Sphere::hit roots (sphere.rs:59-83): false on a negative discriminant, else near/far roots.
 // `self_origin`: the ray starts on this very sphere, so the root that is analytically 0 is dropped (NaN)
 // (in f64 the reference rejects it through ray_t.min = 0.001; in f32 its rounding noise can exceed that).
-__device__ __forceinline__ bool sphere_roots_f32(float3 oc, float3 d, float r, bool self_origin, float* r1, float* r2) {
-    const float a = dot(d, d);
+// a = |d|^2 and inv_a come from the ray set-up.
+__device__ __forceinline__ bool sphere_roots_f32(float3 oc, float3 d, float a, float inv_a, float r, bool self_origin,
+                                                 float* r1, float* r2) {
     const float hb = dot(oc, d);
-    const float inv_a = 1.0f / a;
     // discriminant/a = r^2 - |oc - (hb/a) d|^2 : no cancellation between hb^2 and a*c for distant origins
     const float3 l = fma3(-hb * inv_a, d, oc);
     const float disc = fmaf(r, r, -dot(l, l));
@@ -227,262 +259,219 @@ __device__ __noinline__ bool sphere_roots_f64(float3 o, float3 d, float time, co
     return true;
 }
 
-// ---- one op each; every function advances T.i past the op (or along its skip link) ----
+// ---- primitive tests. Each returns true and the accepted parameter when the op wins over the current best ----
 
-__device__ __forceinline__ void op_inner(Trav& T, float4 w0, float4 w1, float tmin) {
-    T.i = slab(w0, w1, T.o, T.inv, tmin, T.best.t) ? T.i + 2 : fbits(w1.w);
-}
-__device__ __forceinline__ void op_inner_ref(Trav& T, float4 w0, float4 w1, float tmin) {
-    T.i = aabb_hit_reference(w0, w1, T.o, T.inv, tmin, T.best.t) ? T.i + 2 : fbits(w1.w);
-}
-
-__device__ __forceinline__ void op_sphere(const DevScene& S, Trav& T, float4 w0, float4 w1, float time, float tmin, int origin) {
-    const uint32_t flags = ((uint32_t)fbits(w0.w) >> 4) & 15u;
-    const bool moving = flags & FLAG_MOVING;
-    const bool self_origin = (origin >> 3) == T.i && origin >= 0;
+// Sphere::hit (sphere.rs:59-89). w2 (center_vec) is fetched only for a moving sphere.
+template <class Ops>
+__device__ __forceinline__ bool sphere_test(const DevScene& S, const Ops& ops, uint32_t link, float4 w0, float4 w1, float3 o, float3 d,
+                                            float a, float inv_a, float time, float tmin, float tmax, int origin, float* t_out) {
+    const uint32_t flags = ((uint32_t)fbits(w0.w) >> 12) & 15u;
+    const bool self_origin = starts_on(origin, link);
     float r1, r2;
     bool ok;
-    if (flags & FLAG_PRECISE) {
-        ok = sphere_roots_f64(T.o, T.d, time, S.precise + 2 * fbits(w1.w), moving, self_origin, &r1, &r2);
+    if (flags == 0u) {   // the common case first: a static f32 sphere
+        ok = sphere_roots_f32(o - f3(w0), d, a, inv_a, w1.x, self_origin, &r1, &r2);
+    } else if (flags & FLAG_PRECISE) {
+        ok = sphere_roots_f64(o, d, time, S.precise + 2 * fbits(w1.w), flags & FLAG_MOVING, self_origin, &r1, &r2);
     } else {
-        float3 c = f3(w0);
-        if (moving) c = fma3(time, f3(__ldg(S.ops + T.i + 2)), c);  // sphere.rs:53-55
-        ok = sphere_roots_f32(T.o - c, T.d, w1.x, self_origin, &r1, &r2);
+        const float3 c = fma3(time, f3(ops((link & kLinkMask) + 32u)), f3(w0));   // sphere.rs:53-55
+        ok = sphere_roots_f32(o - c, d, a, inv_a, w1.x, self_origin, &r1, &r2);
     }
-    if (ok) {
-        float root = r1;  // ray_t.surrounds: open interval (sphere.rs:78-83)
-        if (!(tmin < root && root < T.best.t)) root = r2;
-        if (tmin < root && root < T.best.t) { T.best.t = root; T.best.op = T.i; T.best.xf = T.cur_xf; }
-    }
-    T.i += moving ? 3 : 2;
+    if (!ok) return false;
+    float root = r1;  // ray_t.surrounds: open interval (sphere.rs:78-83)
+    if (!(tmin < root && root < tmax)) root = r2;
+    *t_out = root;
+    return tmin < root && root < tmax;
 }
 
-__device__ __forceinline__ void op_quad(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin, int origin) {
+// Quad::hit (quad.rs:97-133).
+template <class Ops>
+__device__ __forceinline__ bool quad_test(const Ops& ops, uint32_t link, float4 w0, float4 w1, float3 o, float3 d, float tmin,
+                                          float tmax, int origin, float* t_out) {
     const float3 n = f3(w0);
-    const float denom = dot(n, T.d);
-    const float4 w3 = __ldg(S.ops + T.i + 3);
-    const bool self_origin = (origin >> 3) == T.i && origin >= 0;    // a ray cannot re-hit the plane it starts on
-    if (!(fabsf(denom) < 1e-8f) && !self_origin) {                   // quad.rs:110-112
-        const float t = (w3.x - dot(n, T.o)) / denom;
-        if (tmin <= t && t <= T.best.t) {                             // ray_t.contains: closed (quad.rs:115)
-            const float4 w2 = __ldg(S.ops + T.i + 2);
-            const float3 p = fma3(t, T.d, T.o);
-            const float alpha = dot(f3(w1), p) + w1.w;
-            const float beta = dot(f3(w2), p) + w2.w;
-            if (!(alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f)) { T.best.t = t; T.best.op = T.i; T.best.xf = T.cur_xf; }
-        }
-    }
-    T.i += 4;
+    const float denom = dot(n, d);
+    const uint32_t at = link & kLinkMask;
+    const float4 w3 = ops(at + 48u);
+    if (fabsf(denom) < 1e-8f || starts_on(origin, link)) return false;   // quad.rs:110-112; a ray cannot re-hit the plane it starts on
+    const float t = (w3.x - dot(n, o)) / denom;
+    if (!(tmin <= t && t <= tmax)) return false;                          // ray_t.contains: closed (quad.rs:115)
+    const float4 w2 = ops(at + 32u);
+    const float3 p = fma3(t, d, o);
+    const float alpha = dot(f3(w1), p) + w1.w;
+    const float beta = dot(f3(w2), p) + w2.w;
+    *t_out = t;
+    return !(alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f);
 }
 
-// Quad::cube's six quads (quad.rs:45-93) as one slab test: the nearest face hit inside [tmin, best.t] is the
-// entry plane if it lies in the interval, else the exit plane (HittableList::hit keeps the closest, closed interval).
-__device__ __forceinline__ void op_box(Trav& T, float4 w0, float4 w1, float tmin, int origin) {
+// Quad::cube's six quads (quad.rs:45-93) as one slab test: the nearest face hit inside [tmin, tmax] is the entry
+// plane if it lies in the interval, else the exit plane (HittableList::hit keeps the closest, closed interval).
+// te / tx come from slab_ch on the UNPADDED centre / half extent: good to ~2^-23 (|o| + |c|) / |d_k|, which is what
+// decides hit / miss at the box's edges and the order of two candidates; the hit record takes its t from the exact
+// corners (finalize_hit). A ray that starts on a face of this box goes through the exact form below instead.
+__device__ __forceinline__ bool box_accept(float te, float tx, float tmin, float tmax, float* t_out) {
+    float t = te;
+    if (!(tmin <= t && t <= tmax)) t = tx;
+    *t_out = t;
+    return te <= tx && tmin <= t && t <= tmax;
+}
+// lo = w2.xyz, hi = w3.xyz (exact corners)
+__device__ __forceinline__ bool box_test_from_face(float4 lo, float4 hi, float3 o, float3 inv, float tmin, float tmax, int face,
+                                                   float* t_out) {
     float te, tx;
-    slab_interval(w0, w1, T.o, T.inv, &te, &tx);
-    if (te <= tx) {
-        if ((origin >> 3) == T.i && origin >= 0) {   // ray starts on a face of this box: that plane cannot be hit again
-            const int face = origin & 7;             // 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y
-            const int axis = (face == 1 || face == 3) ? 0 : (face >= 4 ? 1 : 2);
-            const bool max_side = face == 0 || face == 1 || face == 4;
-            const float plane = axis == 0 ? (max_side ? w1.x : w0.x) : axis == 1 ? (max_side ? w1.y : w0.y) : (max_side ? w1.z : w0.z);
-            const float oa = axis == 0 ? T.o.x : axis == 1 ? T.o.y : T.o.z;
-            const float ia = axis == 0 ? T.inv.x : axis == 1 ? T.inv.y : T.inv.z;
-            const float t_self = (plane - oa) * ia;
-            const float nan = __int_as_float(0x7fc00000);
-            if (te == t_self) te = nan;
-            if (tx == t_self) tx = nan;
-        }
-        float t = te;
-        if (!(tmin <= t && t <= T.best.t)) t = tx;
-        if (tmin <= t && t <= T.best.t) { T.best.t = t; T.best.op = T.i; T.best.xf = T.cur_xf; }
-    }
-    T.i += 3;
+    slab_interval(lo, hi, o, inv, &te, &tx);
+    if (!(te <= tx)) return false;
+    // the plane the ray starts on cannot be hit again: 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y
+    const int axis = (face == 1 || face == 3) ? 0 : (face >= 4 ? 1 : 2);
+    const bool max_side = face == 0 || face == 1 || face == 4;
+    const float plane = axis == 0 ? (max_side ? hi.x : lo.x) : axis == 1 ? (max_side ? hi.y : lo.y) : (max_side ? hi.z : lo.z);
+    const float oa = axis == 0 ? o.x : axis == 1 ? o.y : o.z;
+    const float ia = axis == 0 ? inv.x : axis == 1 ? inv.y : inv.z;
+    const float t_self = (plane - oa) * ia;
+    const float nan = __int_as_float(0x7fc00000);
+    if (te == t_self) te = nan;
+    if (tx == t_self) tx = nan;
+    float t = te;
+    if (!(tmin <= t && t <= tmax)) t = tx;
+    *t_out = t;
+    return tmin <= t && t <= tmax;
 }
 
-// Translate::hit / RotateY::hit (hittable.rs:96-111,159-193). The box is tested with the current ray (the space the
-// instance sits in); the transform stored in the op is the composition of all enclosing instances, applied to the
-// WORLD ray, so an instance nested in another instance's subtree needs no stack of saved rays.
-__device__ __forceinline__ void op_xform_enter(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin) {
-    if (slab(w0, w1, T.o, T.inv, tmin, T.best.t)) {
-        const float4 w2 = __ldg(S.ops + T.i + 2), w3 = __ldg(S.ops + T.i + 3);
-        T.o = xform_point(T.so, w2, w3);     // hittable.rs:98,164-168
-        T.d = xform_dir(T.sd, w2, w3);
-        T.inv = safe_inv(T.d);
-        T.cur_xf = T.i;
-        T.i += 4;
-    } else {
-        T.i = fbits(w1.w);
-    }
-}
-
-// Back in the enclosing space: the world ray, or the world ray through the parent instance named by the exit op.
-__device__ __forceinline__ void xform_restore(const DevScene& S, Trav& T, float3 wo, float3 wd, int parent) {
-    T.o = wo; T.d = wd;
-    if (parent >= 0) {
-        const float4 p2 = __ldg(S.ops + parent + 2), p3 = __ldg(S.ops + parent + 3);
-        T.o = xform_point(wo, p2, p3);
-        T.d = xform_dir(wd, p2, p3);
-    }
-    T.inv = safe_inv(T.d);
-    T.cur_xf = parent;
-}
-__device__ __forceinline__ void op_xform_exit(const DevScene& S, Trav& T, float4 w0) {
-    xform_restore(S, T, T.so, T.sd, fbits(w0.x));
-    T.i += 2;
-}
-
-// INNER / BOX / XFORM_ENTER / XFORM_EXIT in one body that shares the slab arithmetic (the render kernel's
-// "slab class"). Returns the class of the lane's next op, read from the header's successor bits.
-// `world(o, d)` fetches the world ray (the render kernels keep it out of registers); it is called only where an
-// instance is entered from inside another one or left.
-template <class WorldRay>
-__device__ __forceinline__ uint32_t op_slab_class(const DevScene& S, Trav& T, float4 w0, float4 w1, float tmin, int origin, WorldRay world) {
-    const uint32_t hdr = (uint32_t)fbits(w0.w);
-    const uint32_t kind = hdr & 15u;
-    const uint32_t ft = (hdr >> 8) & 7u, sk = (hdr >> 11) & 7u;
-    if (kind == OP_XFORM_EXIT) {
-        float3 wo, wd;
-        world(wo, wd);
-        xform_restore(S, T, wo, wd, fbits(w0.x));
-        T.i += 2;
-        return ft;
-    }
-    if (kind == OP_INNER_REF) {
-        const bool pass = aabb_hit_reference(w0, w1, T.o, T.inv, tmin, T.best.t);
-        T.i = pass ? T.i + 2 : fbits(w1.w);
-        return pass ? ft : sk;
-    }
-    float te, tx;
-    slab_interval(w0, w1, T.o, T.inv, &te, &tx);
-    if (kind == OP_BOX) {
-        if ((origin >> 3) == T.i && origin >= 0) {   // rare: the ray starts on a face of this box
-            op_box(T, w0, w1, tmin, origin);
-            return ft;
-        }
-        float t = te;
-        if (!(tmin <= t && t <= T.best.t)) t = tx;
-        if (te <= tx && tmin <= t && t <= T.best.t) { T.best.t = t; T.best.op = T.i; T.best.xf = T.cur_xf; }
-        T.i += 3;
-        return ft;
-    }
-    const float ce = fmaxf(te, tmin), cx = fminf(tx, T.best.t);
-    const bool hit = ce <= cx * 1.0000012f + 1e-30f || ce <= cx;
-    if (!hit) { T.i = fbits(w1.w); return sk; }
-    if (kind == OP_INNER) { T.i += 2; return ft; }
-    const float4 w2 = __ldg(S.ops + T.i + 2), w3 = __ldg(S.ops + T.i + 3);   // OP_XFORM_ENTER
-    float3 wo = T.o, wd = T.d;
-    if (T.cur_xf >= 0) world(wo, wd);      // nested: the op holds the composed world -> local transform
-    T.o = xform_point(wo, w2, w3);
-    T.d = xform_dir(wd, w2, w3);
-    T.inv = safe_inv(T.d);
-    T.cur_xf = T.i;
-    T.i += 4;
-    return ft;
-}
-
-__device__ float boundary_closest_t(const DevScene& S, int begin, int end, const Ray& ray, float tmin, float tmax);
+template <class Ops>
+__device__ float boundary_closest_t(const DevScene& S, const Ops& ops, int begin, int end, const Ray& ray, float tmin, float tmax);
 
 // ConstantMedium::hit (constant_medium.rs:34-70); the medium's box was tested by the preceding OP_INNER.
-__device__ __forceinline__ void op_medium(const DevScene& S, Trav& T, float4 w0, float4 w1, float time, float tmin,
-                                          uint4 key, uint32_t seg) {
-    const int bkind = (int)(((uint32_t)fbits(w0.w) >> 4) & 15u);
-    const float4 w2 = __ldg(S.ops + T.i + 2);
+// `at` = byte offset of the op. Returns true and the scatter parameter when the medium wins; *next_word = the op after it.
+template <class Ops>
+__device__ __forceinline__ bool medium_test(const DevScene& S, const Ops& ops, uint32_t at, float4 w0, float4 w1, float3 o, float3 d,
+                                            float a, float inv_a, float time, float tmin, float tmax, uint4 key, uint32_t seg,
+                                            float* t_out, int* next_word) {
+    const int bkind = (int)(((uint32_t)fbits(w0.w) >> 12) & 15u);
+    const float4 w2 = ops(at + 32u);
     float t1, t2;
     bool ok;
-    int next;
     if (bkind == MEDIUM_BOUNDARY_SPHERE) {
         const uint32_t aux = (uint32_t)fbits(w2.w);
         const bool moving = (aux >> 24) & FLAG_MOVING;
         if ((aux >> 24) & FLAG_PRECISE) {
-            ok = sphere_roots_f64(T.o, T.d, time, S.precise + 2 * (aux & 0xffffffu), moving, false, &t1, &t2);
+            ok = sphere_roots_f64(o, d, time, S.precise + 2 * (aux & 0xffffffu), moving, false, &t1, &t2);
         } else {
             float3 c = f3(w1);
             if (moving) c = fma3(time, f3(w2), c);
-            ok = sphere_roots_f32(T.o - c, T.d, w1.w, false, &t1, &t2);
+            ok = sphere_roots_f32(o - c, d, a, inv_a, w1.w, false, &t1, &t2);
         }
         // hit1 over the universe takes the near root; hit2 needs a root > hit1.t + 0.0001
         ok = ok && (t2 > t1 + 0.0001f);
-        next = T.i + 3;
+        *next_word = (int)(at >> 4) + 3;
     } else if (bkind == MEDIUM_BOUNDARY_XBOX) {
         // both boundary hits of a (rotated, translated) cube from one slab test in the cube's frame
-        const float4 lo = __ldg(S.ops + T.i + 3), hi = __ldg(S.ops + T.i + 4);
-        const float3 lo_ = xform_point(T.o, w1, w2), ld_ = xform_dir(T.d, w1, w2);
+        const float4 lo = ops(at + 48u), hi = ops(at + 64u);
+        const float3 lo_ = xform_point(o, w1, w2), ld_ = xform_dir(d, w1, w2);
         slab_interval(lo, hi, lo_, safe_inv(ld_), &t1, &t2);
         const float inf = __int_as_float(0x7f800000);
         ok = (t1 <= t2) && (t2 >= t1 + 0.0001f) && fabsf(t1) < inf && fabsf(t2) < inf;   // hit2: closed interval from hit1.t + 0.0001
-        next = T.i + 5;
+        *next_word = (int)(at >> 4) + 5;
     } else {
-        Ray lr; lr.o = T.o; lr.d = T.d; lr.time = time;
+        Ray lr; lr.o = o; lr.d = d; lr.time = time;
         const float inf = __int_as_float(0x7f800000);
-        t1 = boundary_closest_t(S, fbits(w1.x), fbits(w1.y), lr, -inf, inf);
+        t1 = boundary_closest_t(S, ops, fbits(w1.x), fbits(w1.y), lr, -inf, inf);
         ok = (t1 == t1);
-        if (ok) { t2 = boundary_closest_t(S, fbits(w1.x), fbits(w1.y), lr, t1 + 0.0001f, inf); ok = (t2 == t2); }
-        next = fbits(w1.y);
+        if (ok) { t2 = boundary_closest_t(S, ops, fbits(w1.x), fbits(w1.y), lr, t1 + 0.0001f, inf); ok = (t2 == t2); }
+        *next_word = fbits(w1.y);
     }
-    if (ok) {
-        t1 = fmaxf(t1, tmin);
-        t2 = fminf(t2, T.best.t);
-        if (t1 < t2) {
-            t1 = fmaxf(t1, 0.0f);
-            const float ray_length = sqrtf(dot(T.d, T.d));
-            const float inside = (t2 - t1) * ray_length;
-            const float u = u01(draw(key, seg, P_MEDIUM + (uint32_t)fbits(w0.z)).x);
-            const float hit_distance = w0.x * logf(u);   // drawn only on this branch (constant_medium.rs:48)
-            if (hit_distance <= inside) { T.best.t = t1 + hit_distance / ray_length; T.best.op = T.i; T.best.xf = T.cur_xf; }
-        }
-    }
-    T.i = next;
-}
-
-__device__ __forceinline__ void trav_begin(Trav& T, const Ray& ray, int begin, float tmax) {
-    T.o = ray.o; T.d = ray.d;
-    T.inv = safe_inv(ray.d);
-    T.so = ray.o; T.sd = ray.d;
-    T.cur_xf = -1;
-    T.i = begin;
-    T.best.t = tmax; T.best.op = -1; T.best.xf = -1;
+    if (!ok) return false;
+    t1 = fmaxf(t1, tmin);
+    t2 = fminf(t2, tmax);
+    if (!(t1 < t2)) return false;
+    t1 = fmaxf(t1, 0.0f);
+    const float ray_length = sqrtf(a);
+    const float inside = (t2 - t1) * ray_length;
+    const float u = u01(draw(key, seg, P_MEDIUM + (uint32_t)fbits(w0.z)).x);
+    const float hit_distance = w0.x * logf(u);   // drawn only on this branch (constant_medium.rs:48)
+    *t_out = t1 + hit_distance / ray_length;
+    return hit_distance <= inside;
 }
 
 // Hoisted (world-space) media: evaluated before the traversal of every segment; each may lower best.t.
-__device__ __forceinline__ void media_prepass(const DevScene& S, Trav& T, float time, float tmin, uint4 key, uint32_t seg) {
-    const int begin = T.i;
+template <class Ops>
+__device__ __forceinline__ void media_prepass(const DevScene& S, const Ops& ops, float3 o, float3 d, float a, float inv_a, float time,
+                                              float tmin, uint4 key, uint32_t seg, Best& best) {
     for (int m = 0; m < S.n_media; ++m) {
-        T.i = S.media_op[m];
-        op_medium(S, T, __ldg(S.ops + T.i), __ldg(S.ops + T.i + 1), time, tmin, key, seg);
+        const uint32_t at = (uint32_t)S.media_op[m] << 4;
+        float t;
+        int next;
+        if (medium_test(S, ops, at, ops(at), ops(at + 16u), o, d, a, inv_a, time, tmin, best.t, key, seg, &t, &next)) {
+            best.t = t; best.op = S.media_op[m]; best.xf = -1;
+        }
     }
-    T.i = begin;
 }
 
-// Generic loop (parity kernels, medium boundary programs). WORLD = false: t only, no media.
-template <bool WORLD>
-__device__ __forceinline__ void traverse(const DevScene& S, int begin, int end, const Ray& ray, float tmin, float tmax,
+// Generic loop (parity kernels, medium boundary programs): every lane walks its own ray to the end. WORLD = false: t only,
+// no media. `begin` / `end` are word indices.
+template <bool WORLD, class Ops>
+__device__ __forceinline__ void traverse(const DevScene& S, const Ops& ops, int begin, int end, const Ray& ray, float tmin, float tmax,
                                          Best& best, int origin, uint4 key, uint32_t seg) {
-    Trav T;
-    trav_begin(T, ray, begin, tmax);
-    if (WORLD) media_prepass(S, T, ray.time, tmin, key, seg);
-    const float4* __restrict__ ops = S.ops;
-    while (T.i < end) {
-        const float4 w0 = __ldg(ops + T.i);
-        const float4 w1 = __ldg(ops + T.i + 1);
-        const uint32_t kind = (uint32_t)fbits(w0.w) & 15u;
-        if (kind == OP_INNER) op_inner(T, w0, w1, tmin);
-        else if (kind == OP_INNER_REF) op_inner_ref(T, w0, w1, tmin);
-        else if (kind == OP_SPHERE) op_sphere(S, T, w0, w1, ray.time, tmin, origin);
-        else if (kind == OP_BOX) op_box(T, w0, w1, tmin, origin);
-        else if (kind == OP_QUAD) op_quad(S, T, w0, w1, tmin, origin);
-        else if (kind == OP_XFORM_ENTER) op_xform_enter(S, T, w0, w1, tmin);
-        else if (kind == OP_XFORM_EXIT) op_xform_exit(S, T, w0);
-        else if (WORLD) op_medium(S, T, w0, w1, ray.time, tmin, key, seg);
-        else T.i = end;   // a medium inside a boundary program is rejected at upload
+    float3 o = ray.o, d = ray.d;
+    RaySetup R = ray_setup(o, d);
+    int cur_xf = -1;
+    best.t = tmax; best.op = -1; best.xf = -1;
+    if (WORLD) media_prepass(S, ops, o, d, R.a, R.inv_a, ray.time, tmin, key, seg, best);
+    uint32_t at = (uint32_t)begin << 4;
+    const uint32_t stop = (uint32_t)end << 4;
+    while (at < stop) {
+        const float4 w0 = ops(at), w1 = ops(at + 16u);
+        const uint32_t hdr = (uint32_t)fbits(w0.w);
+        const uint32_t kind = (hdr >> 8) & 15u;
+        uint32_t next = at + (hdr & 0xffu);
+        float t;
+        if (kind == OP_INNER || kind == OP_BOX || kind == OP_XFORM_ENTER) {
+            float te, tx;
+            slab_ch(w0, w1, R.inv, R.oi, &te, &tx);
+            if (kind == OP_BOX) {
+                bool win;
+                if (starts_on(origin, at)) win = box_test_from_face(ops(at + 32u), ops(at + 48u), o, R.inv, tmin, best.t, origin & 7, &t);
+                else win = box_accept(te, tx, tmin, best.t, &t);
+                if (win) { best.t = t; best.op = (int)(at >> 4); best.xf = cur_xf; }
+            } else if (!cull_pass(te, tx, tmin, best.t, R.eps)) {
+                next = (uint32_t)fbits(w1.w) & kLinkMask;
+            } else if (kind == OP_XFORM_ENTER) {   // Translate::hit / RotateY::hit (hittable.rs:96-111,159-193)
+                const float4 w2 = ops(at + 32u), w3 = ops(at + 48u);
+                o = xform_point(ray.o, w2, w3);    // the op holds the composed world -> local transform
+                d = xform_dir(ray.d, w2, w3);
+                R = ray_setup(o, d);
+                cur_xf = (int)(at >> 4);
+            }
+        } else if (kind == OP_SPHERE) {
+            if (sphere_test(S, ops, at, w0, w1, o, d, R.a, R.inv_a, ray.time, tmin, best.t, origin, &t)) { best.t = t; best.op = (int)(at >> 4); best.xf = cur_xf; }
+        } else if (kind == OP_QUAD) {
+            if (quad_test(ops, at, w0, w1, o, d, tmin, best.t, origin, &t)) { best.t = t; best.op = (int)(at >> 4); best.xf = cur_xf; }
+        } else if (kind == OP_INNER_REF) {
+            if (!aabb_hit_reference(w0, w1, o, R.inv, tmin, best.t)) next = (uint32_t)fbits(w1.w) & kLinkMask;
+        } else if (kind == OP_XFORM_EXIT) {    // back in the enclosing space: the world ray, or the world ray through the parent
+            const int parent = fbits(w0.x);
+            o = ray.o; d = ray.d;
+            if (parent >= 0) {
+                const float4 p2 = ops(((uint32_t)parent << 4) + 32u), p3 = ops(((uint32_t)parent << 4) + 48u);
+                o = xform_point(ray.o, p2, p3);
+                d = xform_dir(ray.d, p2, p3);
+            }
+            R = ray_setup(o, d);
+            cur_xf = parent;
+        } else if (WORLD) {                    // OP_MEDIUM in the stream
+            int nw;
+            if (medium_test(S, ops, at, w0, w1, o, d, R.a, R.inv_a, ray.time, tmin, best.t, key, seg, &t, &nw)) { best.t = t; best.op = (int)(at >> 4); best.xf = cur_xf; }
+            next = (uint32_t)nw << 4;
+        } else {
+            next = stop;   // a medium inside a boundary program is rejected at upload
+        }
+        at = next;
     }
-    best = T.best;
 }
 
 // Closest t of a medium's boundary program (t only; constant_medium.rs:35-39 needs nothing else).
-__device__ __noinline__ float boundary_closest_t(const DevScene& S, int begin, int end, const Ray& ray, float tmin, float tmax) {
+template <class Ops>
+__device__ __noinline__ float boundary_closest_t(const DevScene& S, const Ops& ops, int begin, int end, const Ray& ray, float tmin, float tmax) {
     Best b;
-    traverse<false>(S, begin, end, ray, tmin, tmax, b, -1, make_uint4(0, 0, 0, 0), 0u);
+    traverse<false>(S, ops, begin, end, ray, tmin, tmax, b, -1, make_uint4(0, 0, 0, 0), 0u);
     return b.op >= 0 ? b.t : __int_as_float(0x7fc00000);
 }
 
@@ -516,32 +505,32 @@ __device__ __noinline__ float3 precise_sphere_normal(const double4* pr, bool mov
               (float)((((double)o.z - cz) + (double)t * (double)d.z) * inv_r));
 }
 
-__device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, const Best& best, HitRec& h) {
-    const float4* __restrict__ ops = S.ops;
+template <class Ops>
+__device__ __forceinline__ void finalize_hit(const DevScene& S, const Ops& ops, const Ray& ray, const Best& best, HitRec& h) {
     float3 o = ray.o, d = ray.d;
     float4 x2, x3;
     if (best.xf >= 0) {
-        x2 = __ldg(ops + best.xf + 2); x3 = __ldg(ops + best.xf + 3);
+        x2 = ops(((uint32_t)best.xf << 4) + 32u); x3 = ops(((uint32_t)best.xf << 4) + 48u);
         o = xform_point(o, x2, x3);
         d = xform_dir(d, x2, x3);
     }
-    const float4 w0 = __ldg(ops + best.op), w1 = __ldg(ops + best.op + 1);
+    const uint32_t at = (uint32_t)best.op << 4;
+    const float4 w0 = ops(at), w1 = ops(at + 16u);
     const uint32_t hdr = (uint32_t)fbits(w0.w);
-    const uint32_t kind = hdr & 15u;
-    const float t = best.t;
-    h.t = t;
+    const uint32_t kind = (hdr >> 8) & 15u;
+    float t = best.t;
     h.uv_lazy = false;
     h.u = 0.0f; h.v = 0.0f;
     h.origin = origin_code(best.op, 0);
     float3 outward;
     if (kind == OP_SPHERE) {
-        const uint32_t flags = (hdr >> 4) & 15u;
+        const uint32_t flags = (hdr >> 12) & 15u;
         const float3 pl = fma3(t, d, o);
         if (flags & FLAG_PRECISE) {
             outward = precise_sphere_normal(S.precise + 2 * fbits(w1.w), flags & FLAG_MOVING, o, d, t, ray.time);
         } else {
             float3 c = f3(w0);
-            if (flags & FLAG_MOVING) c = fma3(ray.time, f3(__ldg(ops + best.op + 2)), c);
+            if (flags & FLAG_MOVING) c = fma3(ray.time, f3(ops(at + 32u)), c);
             outward = (pl - c) * (1.0f / w1.x);   // (p - center) / radius, reciprocal-multiply (vec3.rs:244-249)
         }
         h.mat = fbits(w1.y);
@@ -549,7 +538,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, 
         h.uv_lazy = true;
         h.sn = outward;
     } else if (kind == OP_QUAD) {
-        const float4 w2 = __ldg(ops + best.op + 2), w3 = __ldg(ops + best.op + 3);
+        const float4 w2 = ops(at + 32u), w3 = ops(at + 48u);
         const float3 pl = fma3(t, d, o);
         outward = f3(w0);
         h.u = dot(f3(w1), pl) + w1.w;
@@ -557,25 +546,26 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, 
         h.mat = fbits(w3.y);
         h.prim = fbits(w3.z);
     } else if (kind == OP_BOX) {
-        // which face produced t: the plane whose parameter equals t exactly (t was taken from these very values);
-        // on an edge the face that comes later in the list wins (closed interval, hittable.rs:66-71)
+        // The traversal's t for a box is good to a few ulp of the coordinates (box_accept). The record's t is the
+        // parameter of the face plane nearest to it, from the exact corners in the cancellation-free form; on an
+        // edge the face that comes later in the list wins (closed interval, hittable.rs:66-71).
+        const float4 lo = ops(at + 32u), hi = ops(at + 48u);
         const float3 inv = safe_inv(d);
-        const float tx0 = (w0.x - o.x) * inv.x, tx1 = (w1.x - o.x) * inv.x;
-        const float ty0 = (w0.y - o.y) * inv.y, ty1 = (w1.y - o.y) * inv.y;
-        const float tz0 = (w0.z - o.z) * inv.z, tz1 = (w1.z - o.z) * inv.z;
-        // (nearest rather than equal: t was taken from these very expressions during the traversal and is normally
-        // bit-equal to one of them, but the face must not hinge on two inline sites rounding identically)
+        const float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
+        const float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
+        const float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
         int face = 0;
-        float miss = __int_as_float(0x7f800000);
-        { const float m = fabsf(tz1 - t); if (m <= miss) { miss = m; face = 0; } }
-        { const float m = fabsf(tx1 - t); if (m <= miss) { miss = m; face = 1; } }
-        { const float m = fabsf(tz0 - t); if (m <= miss) { miss = m; face = 2; } }
-        { const float m = fabsf(tx0 - t); if (m <= miss) { miss = m; face = 3; } }
-        { const float m = fabsf(ty1 - t); if (m <= miss) { miss = m; face = 4; } }
-        { const float m = fabsf(ty0 - t); if (m <= miss) { miss = m; face = 5; } }
+        float miss = __int_as_float(0x7f800000), tf = t;
+        { const float m = fabsf(tz1 - t); if (m <= miss) { miss = m; face = 0; tf = tz1; } }
+        { const float m = fabsf(tx1 - t); if (m <= miss) { miss = m; face = 1; tf = tx1; } }
+        { const float m = fabsf(tz0 - t); if (m <= miss) { miss = m; face = 2; tf = tz0; } }
+        { const float m = fabsf(tx0 - t); if (m <= miss) { miss = m; face = 3; tf = tx0; } }
+        { const float m = fabsf(ty1 - t); if (m <= miss) { miss = m; face = 4; tf = ty1; } }
+        { const float m = fabsf(ty0 - t); if (m <= miss) { miss = m; face = 5; tf = ty0; } }
+        t = tf;
         const float3 pl = fma3(t, d, o);
-        const float ex = 1.0f / (w1.x - w0.x), ey = 1.0f / (w1.y - w0.y), ez = 1.0f / (w1.z - w0.z);
-        const float ax = (pl.x - w0.x) * ex, ay = (pl.y - w0.y) * ey, az = (pl.z - w0.z) * ez;   // 0..1 along +x,+y,+z
+        const float ex = 1.0f / (hi.x - lo.x), ey = 1.0f / (hi.y - lo.y), ez = 1.0f / (hi.z - lo.z);
+        const float ax = (pl.x - lo.x) * ex, ay = (pl.y - lo.y) * ey, az = (pl.z - lo.z) * ez;   // 0..1 along +x,+y,+z
         outward = f3(0.0f, 0.0f, 0.0f);
         switch (face) {   // (u, v) = (alpha, beta) of the face's quad (quad.rs:55-90)
             case 0: outward.z = 1.0f;  h.u = ax;        h.v = ay; break;
@@ -586,7 +576,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, 
             default: outward.y = -1.0f; h.u = ax;       h.v = az; break;
         }
         h.mat = fbits(w1.w);
-        h.prim = fbits(__ldg(ops + best.op + 2).x) + face;
+        h.prim = fbits(lo.w) + face;
         h.origin = origin_code(best.op, face);
     } else {  // OP_MEDIUM: HitRecord::new(r.at(t), phase, t, r, r.direction) (constant_medium.rs:52-58)
         outward = d;
@@ -594,6 +584,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ray& ray, 
         h.prim = fbits(w0.z);
         h.origin = -1;
     }
+    h.t = t;
     h.front_face = dot(d, outward) < 0.0f;                  // hittable.rs:23
     float3 n = h.front_face ? outward : -outward;
     if (best.xf >= 0) n = xform_dir_back(n, x2, x3);        // hittable.rs:176-179 (Translate leaves the normal alone)

@@ -196,18 +196,34 @@ struct Compiler {
     int here() const { return (int)out->ops.size(); }
     void push(float x, float y, float z, float w) { out->ops.push_back(F4{x, y, z, w}); }
 
-    // {lo.xyz, hdr} {hi.xyz, skip(patched later)}; returns index of word 1
-    int push_box_header(const Box& b, uint32_t hdr) {
-        if (b.valid) {
+    // Cull box of `kind` (OP_INNER / OP_XFORM_ENTER: centre / half extent, padded; OP_INNER_REF: the reference's corners);
+    // w1.w = skip (a word index until the final pass turns it into a link). Returns the index of word 1.
+    int push_box_header(const Box& b, uint32_t kind, int size_words) {
+        const uint32_t hdr = make_hdr(kind, 0, (uint32_t)size_words);
+        if (!b.valid) {  // empty subtree: a box nothing can hit (far < near on every axis, whatever the ray)
+            const float inf = std::numeric_limits<float>::infinity();
+            if (kind == OP_INNER_REF) { push(inf, inf, inf, bits_to_float(hdr)); push(-inf, -inf, -inf, 0.0f); }
+            else { push(0.0f, 0.0f, 0.0f, bits_to_float(hdr)); push(-inf, -inf, -inf, 0.0f); }
+            return here() - 1;
+        }
+        for (int c = 0; c < 3; ++c)
+            if (std::isfinite(b.lo[c]) && std::isfinite(b.hi[c])) scale = std::fmax(scale, std::fmax(std::fabs(b.lo[c]), std::fabs(b.hi[c])));
+        if (kind == OP_INNER_REF) {
             push(round_down(b.lo[0]), round_down(b.lo[1]), round_down(b.lo[2]), bits_to_float(hdr));
             push(round_up(b.hi[0]), round_up(b.hi[1]), round_up(b.hi[2]), 0.0f);
-            for (int c = 0; c < 3; ++c)
-                if (std::isfinite(b.lo[c]) && std::isfinite(b.hi[c])) scale = std::fmax(scale, std::fmax(std::fabs(b.lo[c]), std::fabs(b.hi[c])));
-        } else {  // empty subtree: a box nothing can hit
-            const float inf = std::numeric_limits<float>::infinity();
-            push(inf, inf, inf, bits_to_float(hdr));
-            push(-inf, -inf, -inf, 0.0f);
+            return here() - 1;
         }
+        float c[3], h[3];
+        for (int k = 0; k < 3; ++k) {
+            if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) { c[k] = 0.0f; h[k] = std::numeric_limits<float>::infinity(); continue; }
+            const double cd = 0.5 * (b.lo[k] + b.hi[k]), hd = 0.5 * (b.hi[k] - b.lo[k]);
+            c[k] = (float)cd;
+            // covers the rounding of c, of the per-ray products and of the prim tests (dev_scene.h, CULL BOXES)
+            const double pad = std::ldexp(std::fabs(cd) + hd, -21) + std::fabs((double)c[k] - cd) + 1e-30;
+            h[k] = std::nextafterf((float)(hd + pad), std::numeric_limits<float>::infinity());
+        }
+        push(c[0], c[1], c[2], bits_to_float(hdr));
+        push(h[0], h[1], h[2], 0.0f);
         return here() - 1;
     }
     void patch_skip(int word1) { out->ops[word1].w = int_to_float_bits(here()); }
@@ -226,7 +242,7 @@ struct Compiler {
         if (h.flags & RT_FLAG_MOVING) flags |= FLAG_MOVING;
         int pidx = 0;
         if (wants_precise(h)) { flags |= FLAG_PRECISE; pidx = add_precise(h); }
-        push((float)h.v0[0], (float)h.v0[1], (float)h.v0[2], bits_to_float(make_hdr(OP_SPHERE, flags)));
+        push((float)h.v0[0], (float)h.v0[1], (float)h.v0[2], bits_to_float(make_hdr(OP_SPHERE, flags, (flags & FLAG_MOVING) ? 3 : 2)));
         push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), int_to_float_bits(pidx));
         if (flags & FLAG_MOVING) push((float)h.v1[0], (float)h.v1[1], (float)h.v1[2], 0.0f);
     }
@@ -239,7 +255,7 @@ struct Compiler {
         const double B[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};
         const double a0 = -(A[0] * q[0] + A[1] * q[1] + A[2] * q[2]);
         const double b0 = -(B[0] * q[0] + B[1] * q[1] + B[2] * q[2]);
-        push((float)h.n[0], (float)h.n[1], (float)h.n[2], bits_to_float(make_hdr(OP_QUAD)));
+        push((float)h.n[0], (float)h.n[1], (float)h.n[2], bits_to_float(make_hdr(OP_QUAD, 0, 4)));
         push((float)A[0], (float)A[1], (float)A[2], (float)a0);
         push((float)B[0], (float)B[1], (float)B[2], (float)b0);
         push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), 0.0f);
@@ -263,9 +279,18 @@ struct Compiler {
     void emit_box(int id) {
         const rt_hittable_desc& h = d->hittables[id];
         const int first = d->list_items[h.child];
-        push((float)h.v0[0], (float)h.v0[1], (float)h.v0[2], bits_to_float(make_hdr(OP_BOX)));
-        push((float)h.v1[0], (float)h.v1[1], (float)h.v1[2], int_to_float_bits(d->hittables[first].mat));
-        push(int_to_float_bits(first), 0.0f, 0.0f, 0.0f);
+        // centre / half extent of the f32 corners (what the hit record is computed from), rounded to nearest, NOT padded:
+        // this box is the primitive, not a cull box
+        float cc[3], hh[3];
+        for (int k = 0; k < 3; ++k) {
+            const double lo = (double)(float)h.v0[k], hi = (double)(float)h.v1[k];
+            cc[k] = (float)(0.5 * (lo + hi));
+            hh[k] = (float)(0.5 * (hi - lo));
+        }
+        push(cc[0], cc[1], cc[2], bits_to_float(make_hdr(OP_BOX, 0, 4)));
+        push(hh[0], hh[1], hh[2], int_to_float_bits(d->hittables[first].mat));
+        push((float)h.v0[0], (float)h.v0[1], (float)h.v0[2], int_to_float_bits(first));
+        push((float)h.v1[0], (float)h.v1[1], (float)h.v1[2], 0.0f);
         for (int c = 0; c < 3; ++c) scale = std::fmax(scale, std::fmax(std::fabs(h.v0[c]), std::fabs(h.v1[c])));
     }
 
@@ -299,14 +324,14 @@ struct Compiler {
             Box rb;
             rb.valid = true;
             for (int c = 0; c < 3; ++c) { rb.lo[c] = node.bbox[2 * c]; rb.hi[c] = node.bbox[2 * c + 1]; }
-            const int w1 = push_box_header(rb, make_hdr(OP_INNER_REF));
+            const int w1 = push_box_header(rb, OP_INNER_REF, 2);
             if (node.object >= 0) emit(node.object, in_boundary);
             else { emit_node(node.left, in_boundary); emit_node(node.right, in_boundary); }
             patch_skip(w1);
             return;
         }
         if (node.object >= 0) { emit(node.object, in_boundary); return; }
-        const int w1 = push_box_header(tight_of_node(n), make_hdr(OP_INNER));
+        const int w1 = push_box_header(tight_of_node(n), OP_INNER, 2);
         emit_node(node.left, in_boundary);
         emit_node(node.right, in_boundary);
         patch_skip(w1);
@@ -322,7 +347,7 @@ struct Compiler {
             case RT_HIT_LIST: {
                 if (h.count == 0) break;
                 if (is_cube(id)) { emit_box(id); break; }
-                const int w1 = push_box_header(tight(id), make_hdr(OP_INNER));
+                const int w1 = push_box_header(tight(id), OP_INNER, 2);
                 for (int i = 0; i < h.count; ++i) emit(d->list_items[h.child + i], in_boundary);
                 patch_skip(w1);
                 break;
@@ -336,14 +361,14 @@ struct Compiler {
                 XfParams X;
                 const int cur = fold_xform(id, X.a, X.b, &X.s, &X.c);       // relative to the enclosing space
                 if (in_xform()) X = compose(xf_stack.back().second, X);     // world -> local
-                const int w1 = push_box_header(tight(id), make_hdr(OP_XFORM_ENTER));   // box in the enclosing space
+                const int w1 = push_box_header(tight(id), OP_XFORM_ENTER, 4);   // box in the enclosing space
                 push((float)X.a[0], (float)X.a[1], (float)X.a[2], (float)X.s);
                 push((float)X.b[0], (float)X.b[1], (float)X.b[2], (float)X.c);
                 xf_stack.push_back({w1 - 1, X});
                 emit(cur, in_boundary);
                 xf_stack.pop_back();
                 const int parent = in_xform() ? xf_stack.back().first : -1;
-                push(int_to_float_bits(parent), 0.0f, 0.0f, bits_to_float(make_hdr(OP_XFORM_EXIT)));
+                push(int_to_float_bits(parent), 0.0f, 0.0f, bits_to_float(make_hdr(OP_XFORM_EXIT, 0, 2)));
                 push(0.0f, 0.0f, 0.0f, 0.0f);
                 patch_skip(w1);
                 break;
@@ -362,9 +387,9 @@ struct Compiler {
                 std::vector<F4> saved;
                 int w1 = -1;
                 if (hoist) { saved.swap(out->ops); hoisted_at.push_back((int32_t)hoisted.size()); }
-                else w1 = push_box_header(tight(id), make_hdr(OP_INNER));   // the medium's box, then its body
+                else w1 = push_box_header(tight(id), OP_INNER, 2);   // the medium's box, then its body
                 if (bd.kind == RT_HIT_SPHERE) {
-                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_SPHERE)));
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_SPHERE, 3)));
                     // A medium's entry/exit distances feed a random free-flight comparison, never a surface position, so
                     // f32 roots (relative error 1e-7) are enough even for the r = 5000 fog of final_scene.
                     uint32_t pidx = 0;
@@ -374,13 +399,13 @@ struct Compiler {
                     push((float)bd.v1[0], (float)bd.v1[1], (float)bd.v1[2], int_to_float_bits((int32_t)(pidx | (aux << 24))));
                 } else if (!in_xform() && is_cube(inner)) {
                     const rt_hittable_desc& cube = d->hittables[inner];
-                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_XBOX)));
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_XBOX, 5)));
                     push((float)xa[0], (float)xa[1], (float)xa[2], (float)xs);
                     push((float)xb[0], (float)xb[1], (float)xb[2], (float)xc);
                     push((float)cube.v0[0], (float)cube.v0[1], (float)cube.v0[2], 0.0f);
                     push((float)cube.v1[0], (float)cube.v1[1], (float)cube.v1[2], 0.0f);
                 } else {
-                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_PROGRAM)));
+                    push((float)h.s0, int_to_float_bits(h.mat), int_to_float_bits(id), bits_to_float(make_hdr(OP_MEDIUM, MEDIUM_BOUNDARY_PROGRAM, 3)));
                     const int wb = here();
                     push(0.0f, 0.0f, 0.0f, 0.0f);
                     push(0.0f, 0.0f, 0.0f, 0.0f);
@@ -456,8 +481,13 @@ struct Pruner {
     static void set_int(float* f, int32_t v) { std::memcpy(f, &v, 4); }
 
     double box_area(int i) const {
-        const double ex = (double)in[i + 1].x - in[i].x, ey = (double)in[i + 1].y - in[i].y, ez = (double)in[i + 1].z - in[i].z;
-        if (!(ex >= 0.0) || !(ey >= 0.0) || !(ez >= 0.0)) return 0.0;          // the empty box (inf, -inf)
+        double ex, ey, ez;
+        if (hdr_kind(hdr_of(in[i])) == OP_INNER_REF) {
+            ex = (double)in[i + 1].x - in[i].x; ey = (double)in[i + 1].y - in[i].y; ez = (double)in[i + 1].z - in[i].z;
+        } else {
+            ex = 2.0 * in[i + 1].x; ey = 2.0 * in[i + 1].y; ez = 2.0 * in[i + 1].z;   // centre / half extent
+        }
+        if (!(ex >= 0.0) || !(ey >= 0.0) || !(ez >= 0.0)) return 0.0;          // the empty box
         const double a = 2.0 * (ex * ey + ey * ez + ex * ez);
         return a;                                                               // may be +inf
     }
@@ -466,7 +496,7 @@ struct Pruner {
         std::vector<IrNode> nodes;
         int i = begin;
         while (i < end) {
-            const uint32_t hdr = hdr_of(in[i]), kind = hdr & 15u, flags = (hdr >> 4) & 15u;
+            const uint32_t hdr = hdr_of(in[i]), kind = hdr_kind(hdr), flags = hdr_flags(hdr);
             IrNode n;
             n.kind = kind; n.at = i; n.frozen = frozen;
             int next = i;
@@ -487,10 +517,7 @@ struct Pruner {
                         n.n_words = (int)flags == MEDIUM_BOUNDARY_XBOX ? 5 : 3; next = i + n.n_words;
                     }
                     break;
-                case OP_SPHERE: n.n_words = (flags & FLAG_MOVING) ? 3 : 2; next = i + n.n_words; break;
-                case OP_QUAD: n.n_words = 4; next = i + 4; break;
-                case OP_BOX: n.n_words = 3; next = i + 3; break;
-                default: n.n_words = 2; next = i + 2; break;                     // OP_XFORM_EXIT never appears here
+                default: n.n_words = op_words(kind, flags); next = i + n.n_words; break;   // leaves (OP_XFORM_EXIT never appears here)
             }
             nodes.push_back(std::move(n));
             i = next;
@@ -566,7 +593,7 @@ struct Pruner {
             case OP_MEDIUM: {
                 const int pos = (int)out.size();
                 copy_words(n);
-                if (!n.ch.empty() || ((hdr_of(in[n.at]) >> 4) & 15u) == (uint32_t)MEDIUM_BOUNDARY_PROGRAM) {
+                if (!n.ch.empty() || hdr_flags(hdr_of(in[n.at])) == (uint32_t)MEDIUM_BOUNDARY_PROGRAM) {
                     set_int(&out[pos + 1].x, (int32_t)out.size());
                     emit_list(n.ch, std::numeric_limits<double>::infinity());
                     set_int(&out[pos + 1].y, (int32_t)out.size());
@@ -651,59 +678,52 @@ int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, Compiled
     if (!c.status) c.emit(desc->world, false);
     if (!c.status && out->ops.empty()) {  // empty world: one unhittable node keeps the kernels branch-free
         const float inf = std::numeric_limits<float>::infinity();
-        out->ops.push_back(F4{inf, inf, inf, bits_to_float(make_hdr(OP_INNER))});
+        out->ops.push_back(F4{0.0f, 0.0f, 0.0f, bits_to_float(make_hdr(OP_INNER, 0, 2))});
         out->ops.push_back(F4{-inf, -inf, -inf, int_to_float_bits(2)});
     }
     if (c.status) { msg = c.err; if (err) *err = msg.c_str(); return c.status; }
     if (opt.prune_boxes) prune_stream(&out->ops, opt);
 
-    // successor classes into the header bits (dev_scene.h)
+    // links (dev_scene.h): until here every skip is a word index and no header carries a class. This pass checks every
+    // successor, writes the fall-through class into the headers and turns the skips into complete link words.
     {
         std::vector<F4>& ops = out->ops;
         if (ops.empty()) {   // nothing but hoisted media (or nothing at all): keep one unhittable node
             const float inf = std::numeric_limits<float>::infinity();
-            ops.push_back(F4{inf, inf, inf, bits_to_float(make_hdr(OP_INNER))});
+            ops.push_back(F4{0.0f, 0.0f, 0.0f, bits_to_float(make_hdr(OP_INNER, 0, 2))});
             ops.push_back(F4{-inf, -inf, -inf, int_to_float_bits(2)});
         }
         const int n = (int)ops.size();
+        if ((uint64_t)(n + c.hoisted.size() + 2) * 16u >= (uint64_t)kSlabLimit) {
+            msg = "scene too large: the op stream must stay below 256 MiB"; if (err) *err = msg.c_str(); return RT_ERR_UNSUPPORTED;
+        }
         auto hdr_of = [&](int i) { uint32_t u; std::memcpy(&u, &ops[i].w, 4); return u; };
         auto int_of = [&](float f) { int32_t v; std::memcpy(&v, &f, 4); return v; };
-        auto cls_at = [&](int i) -> uint32_t {
-            if (i >= n) return (uint32_t)CLS_SHADE;
-            const uint32_t kind = hdr_of(i) & 15u;
-            return kind == OP_BOX && opt.box_class ? (uint32_t)CLS_BOX : class_of_kind(kind);
-        };
+        auto cls_at = [&](int i) -> uint32_t { return i >= n ? (uint32_t)CLS_SHADE : class_of_kind(hdr_kind(hdr_of(i))); };
         int i = 0;
         while (i < n) {
             const uint32_t hdr = hdr_of(i);
-            const uint32_t kind = hdr & 15u, flags = (hdr >> 4) & 15u;
-            int size = 2, skip = -1;
-            switch (kind) {
-                case OP_INNER: case OP_INNER_REF: size = 2; skip = int_of(ops[i + 1].w); break;
-                case OP_SPHERE: size = (flags & FLAG_MOVING) ? 3 : 2; break;
-                case OP_QUAD: size = 4; break;
-                case OP_XFORM_ENTER: size = 4; skip = int_of(ops[i + 1].w); break;
-                case OP_XFORM_EXIT: size = 2; break;
-                case OP_MEDIUM: size = (int)flags == MEDIUM_BOUNDARY_XBOX ? 5 : 3; break;
-                case OP_BOX: size = 3; break;
-                default: msg = "internal: bad op kind in stream"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL;
-            }
+            const uint32_t kind = hdr_kind(hdr), flags = hdr_flags(hdr);
+            if (kind > OP_INNER_REF) { msg = "internal: bad op kind in stream"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL; }
+            const int size = op_words(kind, flags);
+            const bool has_skip = kind == OP_INNER || kind == OP_INNER_REF || kind == OP_XFORM_ENTER;
+            const int skip = has_skip ? int_of(ops[i + 1].w) : -1;
             int ft = i + size;
             if (kind == OP_MEDIUM && (int)flags == MEDIUM_BOUNDARY_PROGRAM) ft = int_of(ops[i + 1].y);   // run past the inline program
             // the kernels follow these links without bounds checks: every successor must lie in (i, n]
-            if (i + size > n || ft <= i || ft > n || (skip >= 0 && (skip <= i || skip > n))) {
+            if ((int)hdr_words(hdr) != size || i + size > n || ft <= i || ft > n || (has_skip && (skip <= i || skip > n))) {
                 msg = "internal: op stream link out of range"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL;
             }
             if (kind == OP_MEDIUM && (int)flags == MEDIUM_BOUNDARY_PROGRAM && (int_of(ops[i + 1].x) != i + 3 || ft < i + 3)) {
                 msg = "internal: medium boundary program out of range"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL;
             }
-            const uint32_t ft_cls = cls_at(ft), sk_cls = skip >= 0 ? cls_at(skip) : ft_cls;
-            const uint32_t nh = (hdr & 0xffu) | (ft_cls << 8) | (sk_cls << 11);
+            const uint32_t nh = (hdr & 0x0fffffffu) | (cls_at(ft) << 28);
             std::memcpy(&ops[i].w, &nh, 4);
+            if (has_skip) ops[i + 1].w = bits_to_float(make_link(skip, cls_at(skip)));
             i += size;
         }
         if (i != n) { msg = "internal: op stream walk ended off the end"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL; }
-        out->first_class = cls_at(0);
+        out->first_link = make_link(0, cls_at(0));
         out->n_world_words = n;
         for (int32_t off : c.hoisted_at) out->hoisted_media.push_back(n + off);
         ops.insert(ops.end(), c.hoisted.begin(), c.hoisted.end());

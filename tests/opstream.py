@@ -58,18 +58,57 @@ def u01(x):
     return (x >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
 
 
+LINK_MASK = 0x0FFFFFFF
+SLAB_SLACK = 1.0000012
+OP_WORDS = {OP_INNER: 2, OP_SPHERE: 2, OP_QUAD: 4, OP_XFORM_ENTER: 4, OP_XFORM_EXIT: 2, OP_MEDIUM: 3, OP_BOX: 4, OP_INNER_REF: 2}
+
+
 class Stream:
+    """Header word: [0,8) size in bytes, [8,12) kind, [12,16) flags, [28,32) class of the fall-through successor.
+    Skip links: byte offset | class << 28 (csrc/device/dev_scene.h)."""
+
     def __init__(self, ops):
         self.f = ops["words"].astype(np.float64)           # (N, 4) payloads
         self.i = ops["words"].view(np.int32).reshape(-1, 4)  # same words as integers (headers, links, ids)
         self.n_world = ops["n_world_words"]
         self.media = ops["media_ops"]
+        self.first_link = ops.get("first_link", 0)
 
     def kind(self, idx):
-        return self.i[idx, 3] & 15
+        return (self.i[idx, 3] >> 8) & 15
 
     def flags(self, idx):
-        return (self.i[idx, 3] >> 4) & 15
+        return (self.i[idx, 3] >> 12) & 15
+
+    def size_words(self, idx):
+        return (self.i[idx, 3] & 0xFF) >> 4
+
+    def skip(self, idx):
+        """word index a skip link points to"""
+        return ((self.i[idx + 1, 3].astype(np.int64) & LINK_MASK) >> 4)
+
+    def walk(self):
+        """(word index, kind, flags) of every op of the world program, in stream order."""
+        out, i = [], 0
+        while i < self.n_world:
+            k, fl = int(self.kind(i)), int(self.flags(i))
+            out.append((i, k, fl))
+            i += int(self.size_words(i))
+        return out
+
+
+def _slab_ch(c, h, o, inv):
+    """slab_ch() of rt_kernels.cuh: centre / half-extent form. Returns (te, tx, eps)."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        oi = -o * inv
+        tc = c * inv + oi
+        th = np.abs(h * inv)
+        near, far = tc - th, tc + th
+    te = np.fmax(np.fmax(near[:, 0], near[:, 1]), near[:, 2])   # fmax / fmin drop a NaN operand like f64::max / min
+    tx = np.fmin(np.fmin(far[:, 0], far[:, 1]), far[:, 2])
+    e = np.abs(oi)
+    e = np.where(np.isfinite(e), e, 0.0)
+    return te, tx, 4.76837158e-7 * e.max(axis=1)
 
 
 def _slab_interval(lo, hi, o, inv):
@@ -136,7 +175,7 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
     def medium(rows, at):
         """ConstantMedium::hit for rays `rows` (indices) whose medium op sits at word `at` (array). Returns next index."""
         w0f, w0i = F[at], I[at]
-        bkind = (w0i[:, 3] >> 4) & 15
+        bkind = (w0i[:, 3] >> 12) & 15
         nxt = np.zeros(len(rows), dtype=np.int64)
         t1 = np.full(len(rows), np.nan); t2 = np.full(len(rows), np.nan)
         ok = np.zeros(len(rows), dtype=bool)
@@ -201,38 +240,37 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
         if act.size == 0:
             break
         at = idx[act]
-        kind = I[at, 3] & 15
+        kind = (I[at, 3] >> 8) & 15
         if visits is not None:
             np.add.at(visits, at, 1)
         if trace is not None:
             trace.append((act.copy(), kind.astype(np.int8)))
-        # ---- box-headed ops: INNER, INNER_REF, XFORM_ENTER, BOX
+        # ---- box-headed ops: INNER, XFORM_ENTER, BOX (centre / half extent) and INNER_REF (the reference's corners)
         for k in (OP_INNER, OP_INNER_REF, OP_XFORM_ENTER, OP_BOX):
             m = kind == k
             if not m.any():
                 continue
             bump(KIND_NAMES[k], m)
             r_, a = act[m], at[m]
-            lo, hi = F[a][:, :3], F[a + 1][:, :3]
-            te, tx, pa, pb = _slab_interval(lo, hi, o[r_], inv[r_])
-            if k == OP_BOX:
+            if k == OP_INNER_REF:                      # aabb.rs:64-84: per axis against the original interval
+                _, _, pa, pb = _slab_interval(F[a][:, :3], F[a + 1][:, :3], o[r_], inv[r_])
+                neg = inv[r_] < 0.0
+                near = np.where(neg, pb, pa); far = np.where(neg, pa, pb)
+                miss = (np.fmin(far, best_t[r_][:, None]) <= np.fmax(near, tmin[r_][:, None])).any(axis=1)
+                idx[r_] = np.where(~miss, a + 2, S.skip(a))
+                continue
+            te, tx, eps = _slab_ch(F[a][:, :3], F[a + 1][:, :3], o[r_], inv[r_])
+            if k == OP_BOX:                            # box_accept(): the primitive itself, no slack
                 t = te.copy()
                 bad = ~((tmin[r_] <= t) & (t <= best_t[r_]))
                 t[bad] = tx[bad]
                 win = (te <= tx) & (tmin[r_] <= t) & (t <= best_t[r_])
                 w_ = r_[win]
                 best_t[w_] = t[win]; best_op[w_] = a[win]; best_xf[w_] = cur_xf[w_]
-                idx[r_] = a + 3
+                idx[r_] = a + 4
                 continue
-            if k == OP_INNER_REF:                      # aabb.rs:64-84: per axis against the original interval
-                neg = inv[r_] < 0.0
-                near = np.where(neg, pb, pa); far = np.where(neg, pa, pb)
-                miss = (np.fmin(far, best_t[r_][:, None]) <= np.fmax(near, tmin[r_][:, None])).any(axis=1)
-                passed = ~miss
-            else:
-                ce = np.fmax(te, tmin[r_]); cx = np.fmin(tx, best_t[r_])
-                passed = (ce <= cx * 1.0000012 + 1e-30) | (ce <= cx)
-            skip = I[a + 1, 3].astype(np.int64)
+            passed = np.fmax(te, tmin[r_]) <= np.fmin(tx, best_t[r_]) * SLAB_SLACK + eps     # cull_pass()
+            skip = S.skip(a)
             if k == OP_XFORM_ENTER:
                 idx[r_[~passed]] = skip[~passed]
                 p_ = r_[passed]; ap = a[passed]
@@ -261,7 +299,7 @@ def traverse(S, o, d, time, tmin, tmax, begin=0, end=None, world=True, key=None,
         if m.any():
             bump("sphere", m)
             r_, a = act[m], at[m]
-            flags = (I[a, 3] >> 4) & 15
+            flags = (I[a, 3] >> 12) & 15
             moving = (flags & FLAG_MOVING) != 0
             c = F[a][:, :3].copy()
             if moving.any():
@@ -316,7 +354,7 @@ def hit_batch(S, rays, t_min=0.001, t_max=np.inf, seed=7, counts=None, visits=No
     F, I = S.f, S.i
     rows = np.flatnonzero(hit)
     a = op[rows]
-    kind = I[a, 3] & 15
+    kind = (I[a, 3] >> 8) & 15
     pid = np.full(len(rows), -1, dtype=np.int64)
     m = kind == OP_SPHERE
     pid[m] = I[a[m] + 1, 2]
@@ -333,11 +371,18 @@ def hit_batch(S, rays, t_min=0.001, t_max=np.inf, seed=7, counts=None, visits=No
             x = xf[r_][inx]
             lo_o[inx] = _xform_point(lo_o[inx], F[x + 2], F[x + 3])
             lo_d[inx] = _xform_dir(lo_d[inx], F[x + 2], F[x + 3])
-        _, _, pa, pb = _slab_interval(F[ab][:, :3], F[ab + 1][:, :3], lo_o, _safe_inv(lo_d))
+        _, _, pa, pb = _slab_interval(F[ab + 2][:, :3], F[ab + 3][:, :3], lo_o, _safe_inv(lo_d))   # the exact corners
         tt = t[r_]
-        face = np.zeros(len(r_), dtype=np.int64)       # finalize_hit: later faces of quad.rs:45-93 win on an edge
+        # finalize_hit: the face whose plane parameter is nearest to the traversal's t; later faces of quad.rs:45-93 win ties
+        face = np.zeros(len(r_), dtype=np.int64)
+        miss = np.full(len(r_), np.inf)
         for f, plane in ((0, pb[:, 2]), (1, pb[:, 0]), (2, pa[:, 2]), (3, pa[:, 0]), (4, pb[:, 1]), (5, pa[:, 1])):
-            face[plane == tt] = f
-        pid[m] = I[ab + 2, 0] + face
+            with np.errstate(invalid="ignore"):
+                mm = np.abs(plane - tt)
+            upd = mm <= miss
+            face[upd] = f
+            miss[upd] = mm[upd]
+            out["t"][r_[upd]] = plane[upd]
+        pid[m] = I[ab + 2, 3] + face
     out["prim_id"][rows] = pid
     return out

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(rt):
 
 
 def test_abi_version(rt):
-    assert rt._abi.lib().rt_abi_version() == 1
+    assert rt._abi.lib().rt_abi_version() == 2
 
 
 def test_struct_sizes_match_header(rt):
@@ -77,6 +77,28 @@ def test_product_never_touches_the_oracle():
         assert "liboracle" not in open(os.path.join(ROOT, "include", f)).read()
 
 
+def test_product_library_reads_no_environment():
+    """The drop-in's behaviour must not depend on the host process's environment: every getenv in the library's sources
+    sits inside an #ifdef RT_B200_DEV block (the A/B build), and the default build does not define it."""
+    csrc = os.path.join(ROOT, "rust-tracing_b200", "csrc")
+    for dirpath, _, files in os.walk(csrc):
+        for f in files:
+            if not f.endswith((".cpp", ".cu", ".cuh", ".h")):
+                continue
+            depth = 0
+            for line in open(os.path.join(dirpath, f), errors="replace"):
+                t = line.strip()
+                if t.startswith("#ifdef RT_B200_DEV"):
+                    depth += 1
+                elif depth and t.startswith(("#ifdef", "#ifndef", "#if ")):
+                    depth += 1
+                elif depth and t.startswith("#endif"):
+                    depth -= 1
+                elif "getenv" in t and not t.startswith("//"):
+                    assert depth > 0, f"{f}: getenv outside RT_B200_DEV: {t}"
+    assert "RT_B200_DEV" not in open(os.path.join(ROOT, "rust-tracing_b200", "build.py")).read().split("def build(")[0]
+
+
 @pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="GPU present")
 def test_no_cpu_fallback_without_gpu(rt):
     with pytest.raises(rt._abi.RtError) as e:
@@ -96,5 +118,5 @@ def test_cpp_mirror_header_builds_and_runs(rt, tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([exe, "2"], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
-    assert "25 hittables, 15 bvh nodes -> 46 stream words (2 inner, 6 quad, 2 box, 2 instance ops)" in out.stdout
+    assert "25 hittables, 15 bvh nodes -> 48 stream words (2 inner, 6 quad, 2 box, 2 instance ops)" in out.stdout
     assert ("no GPU" in out.stdout) or ("rendered 200x200" in out.stdout)

@@ -7,14 +7,15 @@ from conftest import small_scene
 
 
 @pytest.fixture
-def unpruned(monkeypatch):
-    """The stream as flattened, before the cull boxes that do not pay for themselves are dropped (prune_stream)."""
-    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
+def unpruned(rt):
+    """Layout flags for the stream as flattened, before the cull boxes that do not pay for themselves are dropped
+    (prune_stream)."""
+    return rt.layout_flags(prune=False)
 
 
 def test_final_scene_layout(rt, unpruned):
     s, _ = small_scene(rt, 8, rt.synthetic_earth(64, 32))
-    L = rt.scene_layout(s)
+    L = rt.scene_layout(s, unpruned)
     assert L["n_box"] == 400                      # 400 Quad::cube lists -> 400 slab primitives (2400 quads in the description)
     assert L["n_quad"] == 1                       # the light
     assert L["n_sphere"] == 1000 + 6              # box of spheres + moving, glass, metal, r=70 boundary, earth, noise
@@ -26,22 +27,21 @@ def test_final_scene_layout(rt, unpruned):
 
 
 def test_other_scenes_layout(rt, unpruned):
-    L0 = rt.scene_layout(small_scene(rt, 0)[0])
+    L0 = rt.scene_layout(small_scene(rt, 0)[0], unpruned)
     assert L0["n_precise_spheres"] == 1 and L0["n_box"] == 0 and L0["n_sphere"] == L0["n_inner"] + 1
-    L6 = rt.scene_layout(small_scene(rt, 6)[0])
+    L6 = rt.scene_layout(small_scene(rt, 6)[0], unpruned)
     assert (L6["n_quad"], L6["n_box"], L6["n_xform"], L6["n_inner"]) == (6, 2, 2, 7)
-    L7 = rt.scene_layout(small_scene(rt, 7)[0])
+    L7 = rt.scene_layout(small_scene(rt, 7)[0], unpruned)
     assert (L7["n_quad"], L7["n_box"], L7["n_xform"], L7["n_medium_hoisted"]) == (6, 0, 0, 2)   # boxes only bound media
 
 
 @pytest.mark.parametrize("idx", range(9))
-def test_box_pruning_drops_only_cull_boxes(rt, idx, monkeypatch):
+def test_box_pruning_drops_only_cull_boxes(rt, idx):
     """prune_stream removes OP_INNER nodes whose expected saving is below their cost (surface-area model); every
     primitive, instance and medium stays, in the same order; OP_INNER_REF nodes (semantics, not culling) stay."""
     s, _ = small_scene(rt, idx, rt.synthetic_earth(64, 32) if idx in (2, 8) else None)
     pruned = rt.scene_layout(s)
-    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
-    full = rt.scene_layout(s)
+    full = rt.scene_layout(s, rt.layout_flags(prune=False))
     for k in ("n_sphere", "n_quad", "n_box", "n_xform", "n_medium_in_stream", "n_medium_hoisted", "n_bvh", "n_precise_spheres"):
         assert pruned[k] == full[k], k
     assert pruned["n_inner"] <= full["n_inner"]
@@ -69,7 +69,7 @@ def test_quads_that_stick_out_of_their_box_get_reference_nodes(rt, unpruned):
         l.add(s.Quad((3, 0, 0), (1, 0, 0), (0, 1, 0), m))
         l.add(s.Sphere((6, 0, 0), 0.5, m))
         s.finish(s.BVHNode(l))
-        return rt.scene_layout(s)
+        return rt.scene_layout(s, unpruned)
     assert layout(0)["n_inner"] == 2          # root + one branch; leaves need no box of their own
     assert layout(1)["n_inner"] == 3          # + the leaf box of the skewed quad
 
@@ -95,13 +95,12 @@ def test_nested_instances_flatten_to_composed_transforms(rt):
     assert rt.scene_layout(s)["n_xform"] == 2
     ops = rt.scene_ops(s)
     W, I = ops["words"], ops["words"].view(np.int32).reshape(-1, 4)
-    kinds = I[:ops["n_world_words"], 3] & 15
-    # walk op by op to find the real op starts
+    kinds = (I[:ops["n_world_words"], 3] >> 8) & 15
+    # walk op by op to find the real op starts (the header's low byte is the op's size in bytes)
     starts, i = [], 0
-    size = {0: 2, 1: 2, 2: 4, 3: 4, 4: 2, 5: 3, 6: 3, 7: 2}
     while i < ops["n_world_words"]:
         starts.append(i)
-        i += size[int(kinds[i])]
+        i += (int(I[i, 3]) & 0xFF) >> 4
     enter = [i for i in starts if kinds[i] == 3]
     exits = [i for i in starts if kinds[i] == 4]
     assert len(enter) == 2 and len(exits) == 2

@@ -74,7 +74,7 @@ def test_reference_nodes_decide_what_a_skewed_quad_shows(rt, ob):
     l.add(s.Sphere((9, 0, 0), 1.0, m))
     s.finish(s.BVHNode(l))
     S = opstream.Stream(rt.scene_ops(s))
-    kinds = S.i[:S.n_world, 3] & 15
+    kinds = np.array([k for _, k, _ in S.walk()])
     assert (kinds == opstream.OP_INNER_REF).sum() >= 2          # root and the quad's own leaf box
     rng = np.random.default_rng(1)
     n = 1 << 14
@@ -145,14 +145,13 @@ def test_stream_walk_nested_instances(rt, ob):
 
 
 @pytest.mark.parametrize("idx", [0, 6, 7, 8])
-def test_pruning_changes_no_hit(rt, earth, idx, monkeypatch):
+def test_pruning_changes_no_hit(rt, earth, idx):
     """prune_stream only removes cull boxes: walked on the same rays, the pruned and the unpruned stream must give
     bit-identical closest hits (same t, same primitive), and the pruned one must test fewer boxes."""
     s, cam = small_scene(rt, idx, earth)
     rays = make_rays(cam, s.desc, 1 << 13, seed=11)
     pruned = opstream.Stream(rt.scene_ops(s))
-    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
-    full = opstream.Stream(rt.scene_ops(s))
+    full = opstream.Stream(rt.scene_ops(s, rt.layout_flags(prune=False)))
     ca, cb = {}, {}
     a = opstream.hit_batch(pruned, rays, seed=11, counts=ca)
     b = opstream.hit_batch(full, rays, seed=11, counts=cb)
@@ -167,22 +166,21 @@ def test_ops_export_argument_checks(rt):
     s, _ = small_scene(rt, 1)
     lib = rt._abi.lib()
     n = C.c_int64()
-    assert lib.rt_scene_ops_export(None, None, 0, C.byref(n), None, None, None, None) == rt._abi.RT_ERR_INVALID_ARGUMENT
-    assert lib.rt_scene_ops_export(C.byref(s.desc), None, 0, None, None, None, None, None) == rt._abi.RT_ERR_INVALID_ARGUMENT
-    assert lib.rt_scene_ops_export(C.byref(s.desc), None, 0, C.byref(n), None, None, None, None) == 0 and n.value > 2
+    assert lib.rt_scene_ops_export(None, 0, None, 0, C.byref(n), None, None, None, None) == rt._abi.RT_ERR_INVALID_ARGUMENT
+    assert lib.rt_scene_ops_export(C.byref(s.desc), 0, None, 0, None, None, None, None, None) == rt._abi.RT_ERR_INVALID_ARGUMENT
+    assert lib.rt_scene_ops_export(C.byref(s.desc), 0, None, 0, C.byref(n), None, None, None, None) == 0 and n.value > 2
     buf = (C.c_float * 8)()
-    assert lib.rt_scene_ops_export(C.byref(s.desc), buf, 2, C.byref(n), None, None, None, None) == rt._abi.RT_ERR_OUT_OF_RANGE
+    assert lib.rt_scene_ops_export(C.byref(s.desc), 0, buf, 2, C.byref(n), None, None, None, None) == rt._abi.RT_ERR_OUT_OF_RANGE
 
 
 @pytest.mark.parametrize("seed", range(100, 124))
-def test_pruning_changes_no_hit_random_scenes(rt, seed, monkeypatch):
+def test_pruning_changes_no_hit_random_scenes(rt, seed):
     """The same invariant over generated scenes (nested instances, skewed quads whose OP_INNER_REF nodes must survive,
     media with generic boundaries): pruned and unpruned streams give bit-identical closest hits."""
     s = random_scene(seed)
     rays = random_rays(rt, np.random.default_rng(seed), 1 << 12)
     pruned = opstream.Stream(rt.scene_ops(s))
-    monkeypatch.setenv("RT_B200_NO_PRUNE", "1")
-    full = opstream.Stream(rt.scene_ops(s))
+    full = opstream.Stream(rt.scene_ops(s, rt.layout_flags(prune=False)))
     a = opstream.hit_batch(pruned, rays, seed=seed)
     b = opstream.hit_batch(full, rays, seed=seed)
     assert np.array_equal(a["hit"], b["hit"]) and np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["t"], b["t"])

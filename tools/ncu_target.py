@@ -37,9 +37,6 @@ def main():
         dt = time.time() - t0
         st = ctx.stats()
         print(f"rep {r}: {cam.shape[0] * cam.shape[1] * a.spp / dt / 1e6:.1f} Mpaths/s  segs/path {st['segments'] / st['paths']:.2f}  mean {img[..., :3].mean() / a.spp:.4f}", flush=True)
-        if os.environ.get("RT_B200_TIMING"):
-            kt = ctx.kernel_times()
-            print(f"   timing: wall {1e3 * dt:.1f} ms  shade {kt['ms_shade']:.1f} ms  extend {kt['ms_extend']:.1f} ms  iterations {kt['iterations']}  launches {st['kernel_launches']}", flush=True)
 
 
 if __name__ == "__main__":
