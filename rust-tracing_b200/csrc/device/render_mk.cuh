@@ -375,8 +375,18 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                             float t;
                             bool win;
                             const int origin = COLD_I(F_ORIGIN);
-                            if (starts_on(origin, link)) win = box_test_from_face(ops(link + 32u), ops(link + 48u), CUR_O(), inv, tmin, best_t, origin & 7, &t);
-                            else win = box_accept(te, tx, tmin, best_t, &t);
+                            if (!starts_on(origin, link)) {
+                                win = box_accept(te, tx, tmin, best_t, &t);
+                            } else {
+                                // The ray starts on a face of this very box. Leaving it (the direction points out of that face,
+                                // as every ray scattered off an opaque box does) it cannot hit the box again; going in
+                                // (refraction) it takes the exact form, which knows the plane it stands on.
+                                const int face = origin & 7;   // 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y
+                                const float ia = (face == 1 || face == 3) ? inv.x : (face >= 4 ? inv.y : inv.z);
+                                const bool max_side = face == 0 || face == 1 || face == 4;
+                                win = (ia > 0.0f) != max_side &&
+                                      box_test_from_face(ops(link + 32u), ops(link + 48u), CUR_O(), inv, tmin, best_t, face, &t);
+                            }
                             if (win) { best_t = t; best_op = (int)(link >> 4); best_xf = COLD_I(F_XF); CNT(K_BOX_HIT); }
                             link = ft;
                         } else if (kind == OP_XFORM_ENTER) {   // Translate::hit / RotateY::hit (hittable.rs:96-111,159-193)

@@ -269,12 +269,11 @@ __device__ __forceinline__ bool sphere_test(const DevScene& S, const Ops& ops, u
     const bool self_origin = starts_on(origin, link);
     float r1, r2;
     bool ok;
-    if (flags == 0u) {   // the common case first: a static f32 sphere
-        ok = sphere_roots_f32(o - f3(w0), d, a, inv_a, w1.x, self_origin, &r1, &r2);
-    } else if (flags & FLAG_PRECISE) {
+    if (flags & FLAG_PRECISE) {
         ok = sphere_roots_f64(o, d, time, S.precise + 2 * fbits(w1.w), flags & FLAG_MOVING, self_origin, &r1, &r2);
     } else {
-        const float3 c = fma3(time, f3(ops((link & kLinkMask) + 32u)), f3(w0));   // sphere.rs:53-55
+        float3 c = f3(w0);
+        if (flags & FLAG_MOVING) c = fma3(time, f3(ops((link & kLinkMask) + 32u)), c);   // sphere.rs:53-55
         ok = sphere_roots_f32(o - c, d, a, inv_a, w1.x, self_origin, &r1, &r2);
     }
     if (!ok) return false;
