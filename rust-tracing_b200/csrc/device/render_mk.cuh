@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
     const DevScene& S = prm_in.scene;
     const float tmin = 0.001f;                     // renderer.rs:144
     const float inf = __int_as_float(0x7f800000);
-    const int slab_fast = prm_in.slab_fast, shade_min = prm_in.shade_min, sphere_reps = prm_in.sphere_reps;
+    const int slab_fast = prm_in.slab_fast, shade_min = prm_in.shade_min, sphere_reps = prm_in.sphere_reps, quad_reps = prm_in.quad_reps;
 
     // hot per-lane state: the cursor, the per-ray constants of the slab test, the closest hit so far
     uint32_t link = CLS_NEED << 28;                // no path yet: wants one
@@ -441,16 +441,20 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                 if (!__any_sync(0xffffffffu, (link >> 28) == CLS_SPHERE)) break;
             }
         } else if (pick == CLS_QUAD) {
-            if ((link >> 28) == CLS_QUAD) {
-                const uint32_t hdr = (uint32_t)fbits(w0.w);
-                CNT(K_QUAD);
-                float t;
-                if (quad_test(ops, link, w0, w1, CUR_O(), CUR_D(), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
-                    best_t = t; best_op = (int)((link & kLinkMask) >> 4); best_xf = COLD_I(F_XF);
-                    CNT(K_QUAD_HIT);
+#pragma unroll 1
+            for (int rep = 0; rep < quad_reps; ++rep) {      // lists of quads sit next to each other in the stream
+                if ((link >> 28) == CLS_QUAD) {
+                    const uint32_t hdr = (uint32_t)fbits(w0.w);
+                    CNT(K_QUAD);
+                    float t;
+                    if (quad_test(ops, link, w0, w1, CUR_O(), CUR_D(), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
+                        best_t = t; best_op = (int)((link & kLinkMask) >> 4); best_xf = COLD_I(F_XF);
+                        CNT(K_QUAD_HIT);
+                    }
+                    link = (link & kLinkMask) + (hdr & kHdrFallThrough);
+                    FETCH_NEXT();
                 }
-                link = (link & kLinkMask) + (hdr & kHdrFallThrough);
-                FETCH_NEXT();
+                if (!__any_sync(0xffffffffu, (link >> 28) == CLS_QUAD)) break;
             }
         } else if (pick == CLS_MEDIUM) {
             if ((link >> 28) == CLS_MEDIUM) {     // a medium that could not be hoisted (inside an instance / generic boundary)

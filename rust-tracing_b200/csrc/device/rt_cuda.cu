@@ -45,7 +45,7 @@ struct RenderParams {
     uint32_t ops_bytes;          // bytes of the op stream staged in shared memory (0: read from global memory)
     int shade_min;               // the shade class may win the vote once this many lanes wait for it
     int slab_fast;               // lanes in the slab class that skip the full vote
-    int sphere_reps;             // consecutive sphere ops per vote
+    int sphere_reps, quad_reps;  // consecutive sphere / quad ops per vote
 };
 
 // op counters of the instrumented kernel (rt_render_count_ops): what the device traversal actually executes
@@ -208,9 +208,9 @@ struct rt_context {
     size_t smem_optin = 0;       // largest dynamic shared memory a CTA may ask for
     // vote parameters of the render kernel (render_mk.cuh) and layout options; the product never reads the environment,
     // the -DRT_B200_DEV build of the library (A/B work) takes them from RT_B200_* variables
-    int shade_min = 24, slab_fast = 14, sphere_reps = 2;
+    int shade_min = 24, slab_fast = 6, sphere_reps = 2, quad_reps = 8;   // measured plateaus: profiles/r2_sweep*.log
     bool hoist_media = true, prune_boxes = true, box_primitives = true, ops_in_smem = true;
-    int chunk = 32;
+    int chunk = 8;
     unsigned int* d_counters = nullptr;        // kLaunchSlots work counters
     unsigned long long* d_stats = nullptr;     // kLaunchSlots x K_NUM
     int last_slot = 0;
@@ -318,6 +318,7 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* v = std::getenv("RT_B200_SHADE_MIN")) c->shade_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("RT_B200_SLAB_FAST")) c->slab_fast = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("RT_B200_SPHERE_REPS")) c->sphere_reps = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("RT_B200_QUAD_REPS")) c->quad_reps = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("RT_B200_NO_BOX")) c->box_primitives = std::atoi(v) == 0;
     if (const char* v = std::getenv("RT_B200_NO_PRUNE")) c->prune_boxes = std::atoi(v) == 0;
     if (const char* v = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(v) == 0;
@@ -530,7 +531,7 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     prm.tiles_x = (prm.cam.width + kTileW - 1) / kTileW;
     prm.tiles_y = (prm.cam.height + kTileH - 1) / kTileH;
     // pool = tile x chunk samples; keep >= 64 pools per resident warp so the tail of the launch (warps running dry
-    // while others still hold a pool) stays near 1%: short renders get small chunks, the 10000-spp bench keeps 32
+    // while others still hold a pool) stays near 1%: short renders get smaller chunks than the default of 8
     const int64_t n_tiles = (int64_t)prm.tiles_x * prm.tiles_y;
     const int64_t resident_warps = (int64_t)c->sm_count * (kRenderThreads / 32);
     int chunk = c->chunk;
@@ -546,6 +547,7 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     prm.shade_min = c->shade_min;
     prm.slab_fast = c->slab_fast;
     prm.sphere_reps = c->sphere_reps;
+    prm.quad_reps = c->quad_reps;
     // the op stream rides in shared memory when it fits beside the per-thread path state and the Perlin tables
     MkSmem lay = mk_smem_layout(s->ops_bytes, s->dev.n_perlin);
     const bool in_smem = c->ops_in_smem && !s->ops_in_global && lay.total <= c->smem_optin;
