@@ -10,7 +10,11 @@ pixel into a device float4 SUM framebuffer (rt_render_accumulate, scene already 
 framebuffers are summed onto rank 0 with one NCCL reduce. `value` is timed with CUDA events on the launching
 stream, max over ranks. `e2e` is the same workload through the C ABI with host buffers: rt_scene_upload (host
 scene description incl. the 61 MB RGB8 earth image -> device) + render + the SUM framebuffer back in host memory.
-One JSON line is printed by rank 0.
+One JSON line is printed by rank 0; at N = 1 it also carries `configs`: every other BASELINE.json config measured in
+the same process after the headline (each a fraction of a second on the GPU), with its own roofline fraction.
+
+At N > 1 the sample range is split in proportion to each rank's warm-up throughput (GPUs of one box differ by a few
+per cent on this kernel; the slowest rank sets the step time): rust_tracing_b200.distributed.shard_samples_weighted.
 """
 import argparse
 import json
@@ -27,6 +31,9 @@ METRIC = "Mpaths/sec (pixels x spp / s) on Book-2 final_scene"
 UNIT = "Mpaths/s"
 WORKLOAD = {"scene": 8, "name": "final_scene", "width": 800, "height": 800, "spp": 10000, "max_depth": 40}
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # SMs x lanes x FMA x max SM clock
+# BASELINE.json configs[0..3] (+ the three textured scenes of configs[1]); name: (scene, width, spp, depth override)
+OTHER_CONFIGS = {"cfg1_random_balls": (0, 400, 100, 50), "cfg2a_checker": (1, 800, 500, 0), "cfg2b_earth": (2, 800, 500, 0),
+                 "cfg2c_perlin": (3, 800, 500, 0), "cfg3_cornell_box": (6, 600, 1000, 50), "cfg4_cornell_smoke": (7, 600, 2000, 0)}
 
 
 def flops_per_path():
@@ -175,6 +182,44 @@ def run_reference(args):
     return 0
 
 
+def measure_other_configs(rt, ctx, torch, earth, peak_tflops):
+    """BASELINE.json's other configs at their full size and spp on this GPU: CUDA events around rt_render_accumulate (scene
+    resident, 2 warm-up launches, best of 3, the L2 flushed in between), device-counted flops per path, roofline fraction."""
+    dev = torch.device(f"cuda:{ctx.device_id}")
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (idx, width, spp, depth) in OTHER_CONFIGS.items():
+        s, cs = rt.builtin_scene(idx, image_width=width, samples_per_pixel=spp, max_depth=depth, earth=earth if idx in (2, 8) else None)
+        cam = rt.Camera(cs)
+        h, w = cam.shape
+        ds = ctx.upload(s)
+        fb = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            ctx.render_accumulate(ds, cam, 0, spp, 0, fb.data_ptr(), stream.cuda_stream)
+        best = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(3):
+            flush.zero_()
+            fb.zero_()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ctx.render_accumulate(ds, cam, 0, spp, 1 + rep, fb.data_ptr(), stream.cuda_stream)
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        ok = bool((fb[..., 3] == spp).all().item())
+        ops = ctx.count_ops(ds, cam, 0, 4, seed=0)
+        fpp = device_flops_per_path(ops)
+        mpaths = h * w * spp / best / 1e3
+        out[name] = {"scene": rt.SCENE_NAMES[idx], "width": w, "height": h, "spp": spp, "max_depth": int(cam.max_depth),
+                     "mpaths": mpaths, "ms": best, "flops_per_path": fpp, "tflops": fpp * mpaths * 1e6 / 1e12,
+                     "roofline_frac": fpp * mpaths * 1e6 / 1e12 / peak_tflops, "sample_count_ok": ok}
+        ds.close()
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -206,6 +251,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=WORKLOAD["spp"], help="debug only: anything but 10000 marks the line invalid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config rows (BASELINE.json configs[0..3]) after the headline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -214,7 +260,7 @@ def main():
     import torch
     import torch.distributed as dist
     import rust_tracing_b200 as rt
-    from rust_tracing_b200.distributed import shard_samples, reduce_to_root
+    from rust_tracing_b200.distributed import shard_samples, shard_samples_weighted, reduce_to_root
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,8 +302,17 @@ def main():
         e2.synchronize()
         return e0.elapsed_time(e2), e0.elapsed_time(e1)
 
-    for _ in range(args.warmup):
-        step(False)
+    share_note = "equal"
+    for k in range(args.warmup):
+        _, kms = step(False)
+        if world > 1 and k == args.warmup - 1:
+            # the last warm-up step doubles as the calibration: split the samples in proportion to each rank's speed
+            rate = torch.zeros(world, dtype=torch.float64, device=dev)
+            rate[rank] = count / max(kms, 1e-6)
+            dist.all_reduce(rate)
+            weights = [float(x) for x in rate.cpu()]
+            begin, count = shard_samples_weighted(spp, weights)[rank]
+            share_note = "proportional to warm-up throughput: " + "/".join(str(c) for _, c in shard_samples_weighted(spp, weights))
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -325,7 +380,7 @@ def main():
         paths_per_launch = h * w * count
         ops = ctx.count_ops(ds, cam, 0, 4, seed=0)          # instrumented kernel, outside every timed region
         dfpp = device_flops_per_path(ops)
-        roofline = {"bound": "fp32", "kernel": "render_kernel_v3", "unit": "TFLOP/s", "peak": peak, "peak_source": peak_src,
+        roofline = {"bound": "fp32", "kernel": "render_kernel_mk", "unit": "TFLOP/s", "peak": peak, "peak_source": peak_src,
                     "peak_nominal": NOMINAL_FP32_TFLOPS,
                     "achieved": dfpp * paths_per_launch / kern_s / 1e12, "frac": dfpp * paths_per_launch / kern_s / 1e12 / peak,
                     "traffic": None, "flops_per_path": dfpp,
@@ -341,6 +396,12 @@ def main():
             roofline["traffic"] = tr.get("dram_bytes_per_path", 0.0) * paths_per_launch
             roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per path from profiles/ncu_traffic.json ("
                                         + str(tr.get("capture")) + ") x paths of this launch; HBM is not the bound of this kernel")
+        configs = None
+        if world == 1 and not args.no_configs:
+            configs = measure_other_configs(rt, ctx, torch, earth, peak)
+            configs["cfg5_final_scene"] = {"scene": "final_scene", "width": w, "height": h, "spp": spp, "mpaths": value,
+                                           "ms": total_ms / args.steps, "flops_per_path": dfpp, "tflops": roofline["achieved"],
+                                           "roofline_frac": roofline["frac"]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import binding as ob
@@ -353,12 +414,14 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": f"synthetic scene (seeded layout, BASELINE.md seeds); earth texels: {earth_src}",
                 "config": {"workload": f"Book-2 final_scene {w}x{h}, {spp} spp, depth {WORKLOAD['max_depth']} (BASELINE.json configs[4])",
-                           "parallelism": f"sample-range sharding x{world}, one NCCL reduce to rank 0",
+                           "parallelism": f"sample-range sharding x{world} ({share_note}), one NCCL reduce to rank 0",
                            "l2": "flushed between timed iterations (256 MiB memset)", "valid": spp == WORKLOAD["spp"]},
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h * w * 16},
-                "gpu_launches": args.steps * (1 if count > 0 else 0),   # render_kernel, once per step on this rank
+                "gpu_launches": args.steps * (1 if count > 0 else 0),   # render_kernel_mk, once per step on this rank
                 "check": check}
+        if configs:
+            line["configs"] = configs
         emit(line)
     barrier()
     if world > 1:

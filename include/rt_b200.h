@@ -19,10 +19,12 @@
  *   rt_render*        the parallel loop renderer.rs:26-49 + ray_color :139-155;
  *                     output is the per-pixel SUM over the sample range, as in
  *                     renderer.rs:39,46 (the caller divides by spp, :57)
+ *   rt_render_multi   the same loop sharded over the GPUs of one process, one ncclReduce to the first
  *   rt_finalize_rgb8  color_to_rgb (color.rs:12-19) applied to sum/spp (renderer.rs:55-58)
  *   rt_hit_batch      Hittable::hit (hittable.rs:45-48) on a ray batch — parity entry point
  *   rt_texture_batch  Texture::value (texture.rs:12-14) on a batch — parity entry point
  *   rt_get_ray_batch  Camera::get_ray (camera.rs:112-126) — parity entry point
+ *   rt_scatter_batch  Material::emitted / scatter (material.rs:26-138) on a batch — parity entry point
  *
  * Conventions: extern "C", POD only, no exceptions cross the boundary. Every
  * function returns 0 on success or a negative rt_status; rt_last_error() gives
@@ -330,6 +332,18 @@ int rt_finalize_rgb8(rt_context* ctx, const void* d_sum_rgba, int64_t n_pixels, 
 int rt_render_rgb8(rt_context* ctx, const rt_scene* scene, const rt_camera_desc* cam,
                    int64_t sample_begin, int64_t sample_count, uint64_t seed, uint8_t* host_rgb8);
 
+/* The multi-GPU form of rt_render for a host that is not Python: one context and one uploaded copy of the
+ * scene per GPU of this process, all driven from the calling thread. The sample range is split across the devices
+ * (weights[i] > 0: in proportion, e.g. to each GPU's measured paths/s; weights == NULL: equally), every device accumulates
+ * its share into its own SUM framebuffer, the partial framebuffers are summed onto the first device with ONE ncclReduce
+ * over NVLink (communicators from ncclCommInitAll, created on first use and cached; libnccl.so.2 is loaded at that
+ * moment - RT_ERR_UNSUPPORTED if the host has none), and the result is copied to host memory. With the keyed RNG the
+ * image is the one a single GPU renders, up to f32 summation order. shares_out (optional, n_devices entries) receives
+ * the sample count each device rendered. */
+int rt_render_multi(rt_context* const* ctxs, const rt_scene* const* scenes, int n_devices, const rt_camera_desc* cam,
+                    int64_t sample_begin, int64_t sample_count, uint64_t seed, const double* weights,
+                    float* host_sum_rgba, int64_t* shares_out);
+
 /* Statistics of the last rt_render_accumulate on this context; waits for the device to go idle first. */
 typedef struct rt_render_stats {
     uint64_t paths;
@@ -352,6 +366,20 @@ int rt_texture_batch(rt_context* ctx, const rt_scene* scene, int tex, const doub
                      int64_t n, double* rgb_out /* n*3 */);
 int rt_get_ray_batch(rt_context* ctx, const rt_camera_desc* cam, const int64_t* pixel_index,
                      const int64_t* sample_index, int64_t n, uint64_t seed, rt_ray_desc* out);
+
+/* Material::emitted + Material::scatter (material.rs:11-16,26-138) on a batch of (incoming ray, hit record) pairs -
+ * parity entry point for the tagged scatter switch. The device's keyed RNG is (seed, pixel[k], sample[k], segment); the
+ * CPU oracle driven by the same key draws the same numbers. out[k].scattered = 0: absorbed (Metal below the surface,
+ * DiffuseLight); ray_out / attenuation are then left zero. */
+typedef struct rt_scatter_desc {
+    rt_ray_desc ray_out;      /* scattered ray (origin = hit point, direction not normalised, time carried over) */
+    double attenuation[3];
+    double emitted[3];        /* Material::emitted(u, v, p): non-zero for DiffuseLight only */
+    int32_t scattered;
+    int32_t _pad;
+} rt_scatter_desc;
+int rt_scatter_batch(rt_context* ctx, const rt_scene* scene, const rt_ray_desc* rays_in, const rt_hit_desc* hits, int64_t n,
+                     uint64_t seed, const uint32_t* pixel, const uint32_t* sample, uint32_t segment, rt_scatter_desc* out);
 
 /* Topology of the device's flattened traversal order for one BVH hittable: for every
  * node in pre-order, its leaf object id or -1. n_out receives the count. */

@@ -170,3 +170,24 @@ def sample(kind, mode, seed, n):
     out = np.empty((n, 3), dtype=np.float64)
     lib().oracle_sample(kind, mode, seed, n, out.ctypes.data)
     return out
+
+
+def scatter_batch(scene_desc, rays, hits, pixel, sample, segment=0, seed=0, mode=0):
+    """oracle_scatter over a batch: same structured layout as rt_scatter_batch (Material::emitted + scatter, material.rs:26-138)."""
+    import rust_tracing_b200._abi as A
+    rays = np.ascontiguousarray(rays, dtype=A.ray_dtype())
+    hits = np.ascontiguousarray(hits, dtype=A.hit_dtype())
+    out = np.zeros(len(rays), dtype=A.scatter_dtype())
+    h = lib()
+    att = (C.c_double * 3)()
+    emi = (C.c_double * 3)()
+    sc = A.RayDesc()
+    for k in range(len(rays)):
+        ok = h.oracle_scatter(C.byref(scene_desc), rays[k:k + 1].ctypes.data, hits[k:k + 1].ctypes.data, C.c_uint64(seed), int(pixel[k]),
+                              int(sample[k]), int(segment), mode, C.byref(sc), att, emi)
+        out["scattered"][k] = ok
+        out["emitted"][k] = emi[:]
+        if ok == 1:
+            out["ray_out"][k] = np.frombuffer(bytes(sc), dtype=A.ray_dtype())[0]
+            out["attenuation"][k] = att[:]
+    return out

@@ -128,6 +128,11 @@ def hit_dtype():
                      ("hit", "i4"), ("front_face", "i4"), ("prim_id", "i4"), ("mat_id", "i4")])
 
 
+def scatter_dtype():
+    import numpy as np
+    return np.dtype([("ray_out", ray_dtype()), ("attenuation", "f8", 3), ("emitted", "f8", 3), ("scattered", "i4"), ("_pad", "i4")])
+
+
 P = C.POINTER
 vp = C.c_void_p
 
@@ -170,6 +175,7 @@ PROTOTYPES = {
                                       P(C.c_int32), P(C.c_uint32)]),
     "rt_render_accumulate": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp, vp]),
     "rt_render": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp]),
+    "rt_render_multi": (C.c_int, [P(vp), P(vp), C.c_int, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, P(C.c_double), vp, P(C.c_int64)]),
     "rt_render_rgb8": (C.c_int, [vp, vp, P(CameraDesc), C.c_int64, C.c_int64, C.c_uint64, vp]),
     "rt_finalize_rgb8": (C.c_int, [vp, vp, C.c_int64, C.c_double, vp, vp]),
     "rt_render_get_stats": (C.c_int, [vp, P(RenderStats)]),
@@ -177,6 +183,7 @@ PROTOTYPES = {
     "rt_hit_batch": (C.c_int, [vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_uint64, vp]),
     "rt_texture_batch": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, vp]),
     "rt_get_ray_batch": (C.c_int, [vp, P(CameraDesc), vp, vp, C.c_int64, C.c_uint64, vp]),
+    "rt_scatter_batch": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_uint64, vp, vp, C.c_uint32, vp]),
     "rt_bvh_export": (C.c_int, [vp, C.c_int, vp, C.c_int32, P(C.c_int32)]),
     "rt_measure_fp32_peak": (C.c_int, [vp, P(C.c_double)]),
 }

@@ -396,6 +396,18 @@ class Context:
                                            out.ctypes.data))
         return out
 
+    def scatter_batch(self, dscene, rays, hits, pixel, sample, segment=0, seed=0):
+        """rt_scatter_batch: Material::emitted / scatter on (ray, hit record) pairs; structured array (A.scatter_dtype())."""
+        rays = np.ascontiguousarray(rays, dtype=A.ray_dtype())
+        hits = np.ascontiguousarray(hits, dtype=A.hit_dtype())
+        pixel = np.ascontiguousarray(pixel, dtype=np.uint32)
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        assert len(rays) == len(hits) == len(pixel) == len(sample)
+        out = np.zeros(len(rays), dtype=A.scatter_dtype())
+        A.check(self._lib.rt_scatter_batch(self._h, dscene._h, rays.ctypes.data, hits.ctypes.data, len(rays), seed,
+                                           pixel.ctypes.data, sample.ctypes.data, int(segment), out.ctypes.data))
+        return out
+
     def bvh_export(self, dscene, bvh_hittable, capacity=1 << 20):
         buf = np.empty(capacity, dtype=np.int32)
         n = C.c_int32()
@@ -406,6 +418,22 @@ class Context:
         v = C.c_double()
         A.check(self._lib.rt_measure_fp32_peak(self._h, C.byref(v)))
         return v.value
+
+
+def render_multi(contexts, dscenes, cam, sample_begin=0, sample_count=None, seed=0, weights=None):
+    """rt_render_multi: one Context + DeviceScene per GPU of this process; returns (host float32 (H, W, 4) sums, shares)."""
+    n = len(contexts)
+    assert n == len(dscenes) and n >= 1
+    if sample_count is None:
+        sample_count = cam.samples_per_pixel
+    h, w = cam.shape
+    out = np.empty((h, w, 4), dtype=np.float32)
+    cs = (C.c_void_p * n)(*[c._h for c in contexts])
+    ss = (C.c_void_p * n)(*[d._h for d in dscenes])
+    ws = (C.c_double * n)(*[float(x) for x in weights]) if weights is not None else None
+    shares = (C.c_int64 * n)()
+    A.check(A.lib().rt_render_multi(cs, ss, n, C.byref(cam), sample_begin, sample_count, seed, ws, out.ctypes.data, shares))
+    return out, [int(x) for x in shares]
 
 
 _default_ctx = {}

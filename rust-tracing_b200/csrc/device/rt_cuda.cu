@@ -12,7 +12,11 @@
 
 #include "../host/host_common.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
+#include <map>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -121,6 +125,38 @@ __global__ void get_ray_kernel(DevCamera C, const int64_t* pixel, const int64_t*
     const Ray r = camera_ray(C, (int)(pixel[k] % C.width), (int)(pixel[k] / C.width), key);
     DevRayIn o;
     o.ox = r.o.x; o.oy = r.o.y; o.oz = r.o.z; o.dx = r.d.x; o.dy = r.d.y; o.dz = r.d.z; o.time = r.time; o.pad = 0.0f;
+    out[k] = o;
+}
+
+struct DevScatterIn { float ox, oy, oz, dx, dy, dz, time; float px, py, pz, nx, ny, nz, t, u, v; int front_face, mat; uint32_t pixel, sample; };
+struct DevScatterOut { float ox, oy, oz, dx, dy, dz, time; float ar, ag, ab, er, eg, eb; int scattered; };
+
+// Material::emitted + Material::scatter through the very shade() the render kernel calls (parity).
+__global__ void scatter_kernel(DevScene S, const DevScatterIn* in, int64_t n, uint64_t seed, uint32_t seg, DevScatterOut* out) {
+    float4* sh_vec = dyn_smem;
+    uint8_t* sh_perm = reinterpret_cast<uint8_t*>(dyn_smem + min(S.n_perlin, kMaxPerlinShared) * 256);
+    stage_perlin(S, sh_vec, sh_perm);
+    PerlinShared P{sh_vec, sh_perm};
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const DevScatterIn r = in[k];
+    Ray ray;
+    ray.o = f3(r.ox, r.oy, r.oz); ray.d = f3(r.dx, r.dy, r.dz); ray.time = r.time;
+    HitRec h;
+    h.p = f3(r.px, r.py, r.pz); h.normal = f3(r.nx, r.ny, r.nz);
+    h.t = r.t; h.u = r.u; h.v = r.v; h.mat = r.mat; h.prim = -1; h.origin = -1;
+    h.front_face = r.front_face != 0; h.uv_lazy = false; h.sn = f3(0.0f, 0.0f, 0.0f);
+    float3 L = f3(0.0f, 0.0f, 0.0f), T = f3(1.0f, 1.0f, 1.0f);
+    const uint4 key = path_key(seed, r.pixel, r.sample);
+    const bool alive = shade(S, P, ray, h, key, seg, L, T);
+    DevScatterOut o;
+    memset(&o, 0, sizeof(o));
+    o.scattered = alive ? 1 : 0;
+    o.er = L.x; o.eg = L.y; o.eb = L.z;
+    if (alive) {
+        o.ox = ray.o.x; o.oy = ray.o.y; o.oz = ray.o.z; o.dx = ray.d.x; o.dy = ray.d.y; o.dz = ray.d.z; o.time = ray.time;
+        o.ar = T.x; o.ag = T.y; o.ab = T.z;
+    }
     out[k] = o;
 }
 
@@ -661,6 +697,122 @@ int rt_render_rgb8(rt_context* c, const rt_scene* s, const rt_camera_desc* cam, 
     return rt_finalize_rgb8(c, c->d_fb, cam->image_width * cam->image_height, (double)sample_count, host_rgb8, nullptr);
 }
 
+// ---- multi-GPU in one process: NCCL through dlopen (no link-time dependency: a single-GPU host needs no libnccl)
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool tried = false;
+};
+NcclApi g_nccl;
+std::map<std::vector<int>, std::vector<ncclComm_t>> g_comms;   // device list -> communicators (kept for the life of the process)
+
+int load_nccl() {
+    if (g_nccl.CommInitAll) return RT_OK;
+    if (!g_nccl.tried) {
+        g_nccl.tried = true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            g_nccl.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.handle) break;
+        }
+        if (g_nccl.handle) {
+            g_nccl.CommInitAll = reinterpret_cast<decltype(g_nccl.CommInitAll)>(dlsym(g_nccl.handle, "ncclCommInitAll"));
+            g_nccl.Reduce = reinterpret_cast<decltype(g_nccl.Reduce)>(dlsym(g_nccl.handle, "ncclReduce"));
+            g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(dlsym(g_nccl.handle, "ncclGroupStart"));
+            g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(dlsym(g_nccl.handle, "ncclGroupEnd"));
+            g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.handle, "ncclGetErrorString"));
+        }
+    }
+    if (!g_nccl.CommInitAll || !g_nccl.Reduce || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+        return fail(RT_ERR_UNSUPPORTED, "rt_render_multi: libnccl.so.2 could not be loaded; more than one GPU needs NCCL");
+    return RT_OK;
+}
+int nccl_fail(ncclResult_t r, const char* what) {
+    return fail(RT_ERR_CUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error"));
+}
+}  // namespace
+
+int rt_render_multi(rt_context* const* ctxs, const rt_scene* const* scenes, int n, const rt_camera_desc* cam, int64_t sample_begin,
+                    int64_t sample_count, uint64_t seed, const double* weights, float* host_sum_rgba, int64_t* shares_out) {
+    if (!ctxs || !scenes || !cam || !host_sum_rgba || n <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_multi: null argument");
+    if (sample_count < 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_multi: bad sample_count");
+    std::vector<int> devices;
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i] || !scenes[i]) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_multi: null context / scene");
+        if (scenes[i]->ctx != ctxs[i]) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_multi: scenes[i] must be uploaded through ctxs[i]");
+        for (int d : devices) if (d == ctxs[i]->device) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_multi: one context per device");
+        devices.push_back(ctxs[i]->device);
+    }
+    // the split: contiguous sample ranges, largest remainders take the leftover samples (distributed.py does the same)
+    std::vector<int64_t> share((size_t)n, 0);
+    {
+        double total = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double w = weights ? weights[i] : 1.0;
+            if (!(w >= 0.0)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_multi: weights must be >= 0");
+            total += w;
+        }
+        if (!(total > 0.0)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_multi: weights sum to zero");
+        std::vector<std::pair<double, int>> rem;
+        int64_t given = 0;
+        for (int i = 0; i < n; ++i) {
+            const double exact = (double)sample_count * (weights ? weights[i] : 1.0) / total;
+            share[i] = (int64_t)exact;
+            given += share[i];
+            rem.push_back({exact - (double)share[i], -i});
+        }
+        std::sort(rem.begin(), rem.end(), [](const auto& a, const auto& b) { return a > b; });
+        for (int64_t k = 0; k < sample_count - given; ++k) share[(size_t)(-rem[(size_t)k % rem.size()].second)]++;
+    }
+    if (shares_out) for (int i = 0; i < n; ++i) shares_out[i] = share[i];
+    if (n == 1) return rt_render(ctxs[0], scenes[0], cam, sample_begin, sample_count, seed, host_sum_rgba);
+    int rc = load_nccl();
+    if (rc < 0) return rc;
+    auto it = g_comms.find(devices);
+    if (it == g_comms.end()) {
+        std::vector<ncclComm_t> comms((size_t)n);
+        const ncclResult_t r = g_nccl.CommInitAll(comms.data(), n, devices.data());
+        if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitAll");
+        it = g_comms.emplace(devices, comms).first;
+    }
+    const size_t npx = (size_t)cam->image_width * (size_t)cam->image_height;
+    int64_t begin = sample_begin;
+    for (int i = 0; i < n; ++i) {          // every device starts on its share; the launches are asynchronous
+        rt_context* c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        if (c->fb_pixels < npx) {
+            cudaFree(c->d_fb);
+            c->d_fb = nullptr;
+            c->fb_pixels = 0;
+            CU(cudaMalloc(&c->d_fb, npx * sizeof(float4)));
+            c->fb_pixels = npx;
+        }
+        CU(cudaMemsetAsync(c->d_fb, 0, npx * sizeof(float4), 0));
+        rc = rt_render_accumulate(c, scenes[i], cam, begin, share[i], seed, c->d_fb, nullptr);
+        if (rc < 0) return rc;
+        begin += share[i];
+    }
+    ncclResult_t r = g_nccl.GroupStart();   // partial sums -> the first device, over NVLink
+    for (int i = 0; i < n && r == ncclSuccess; ++i) {
+        cudaSetDevice(ctxs[i]->device);
+        r = g_nccl.Reduce(ctxs[i]->d_fb, ctxs[0]->d_fb, npx * 4, ncclFloat, ncclSum, 0, it->second[(size_t)i], 0);
+    }
+    const ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclReduce");
+    if (r2 != ncclSuccess) return nccl_fail(r2, "ncclGroupEnd");
+    for (int i = n - 1; i >= 1; --i) {
+        CU(cudaSetDevice(ctxs[i]->device));
+        CU(cudaStreamSynchronize(0));
+    }
+    CU(cudaSetDevice(ctxs[0]->device));
+    CU(cudaMemcpy(host_sum_rgba, ctxs[0]->d_fb, npx * sizeof(float4), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
 int rt_finalize_rgb8(rt_context* c, const void* d_sum_rgba, int64_t n_pixels, double spp, uint8_t* host_rgb8, void* stream_) {
     if (!c || !d_sum_rgba || !host_rgb8) return fail(RT_ERR_INVALID_ARGUMENT, "rt_finalize_rgb8: null argument");
     if (n_pixels <= 0) return RT_OK;
@@ -772,6 +924,55 @@ int rt_get_ray_batch(rt_context* c, const rt_camera_desc* cam, const int64_t* pi
         out[k].origin[0] = h[k].ox; out[k].origin[1] = h[k].oy; out[k].origin[2] = h[k].oz;
         out[k].direction[0] = h[k].dx; out[k].direction[1] = h[k].dy; out[k].direction[2] = h[k].dz;
         out[k].time = h[k].time;
+    }
+    return RT_OK;
+}
+
+int rt_scatter_batch(rt_context* c, const rt_scene* s, const rt_ray_desc* rays_in, const rt_hit_desc* hits, int64_t n, uint64_t seed,
+                     const uint32_t* pixel, const uint32_t* sample, uint32_t segment, rt_scatter_desc* out) {
+    if (!c || !s) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scatter_batch: null argument");
+    if (n <= 0) return n == 0 ? RT_OK : fail(RT_ERR_INVALID_ARGUMENT, "rt_scatter_batch: negative count");
+    if (!rays_in || !hits || !pixel || !sample || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scatter_batch: null buffer");
+    const int n_mats = (int)(s->compiled.materials.size() / 2);
+    std::vector<DevScatterIn> h_in((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+        if (hits[k].mat_id < 0 || hits[k].mat_id >= n_mats) return fail(RT_ERR_OUT_OF_RANGE, "rt_scatter_batch: hit record names an unknown material");
+        DevScatterIn& r = h_in[k];
+        r.ox = (float)rays_in[k].origin[0]; r.oy = (float)rays_in[k].origin[1]; r.oz = (float)rays_in[k].origin[2];
+        r.dx = (float)rays_in[k].direction[0]; r.dy = (float)rays_in[k].direction[1]; r.dz = (float)rays_in[k].direction[2];
+        r.time = (float)rays_in[k].time;
+        r.px = (float)hits[k].p[0]; r.py = (float)hits[k].p[1]; r.pz = (float)hits[k].p[2];
+        r.nx = (float)hits[k].normal[0]; r.ny = (float)hits[k].normal[1]; r.nz = (float)hits[k].normal[2];
+        r.t = (float)hits[k].t; r.u = (float)hits[k].u; r.v = (float)hits[k].v;
+        r.front_face = hits[k].front_face; r.mat = hits[k].mat_id;
+        r.pixel = pixel[k]; r.sample = sample[k];
+    }
+    CU(cudaSetDevice(c->device));
+    DevScatterIn* d_in = nullptr;
+    DevScatterOut* d_out = nullptr;
+    CU(cudaMalloc(&d_in, (size_t)n * sizeof(DevScatterIn)));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n * sizeof(DevScatterOut));
+    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc(scatter)"); }
+    std::vector<DevScatterOut> h_out((size_t)n);
+    e = cudaMemcpy(d_in, h_in.data(), (size_t)n * sizeof(DevScatterIn), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)perlin_smem_bytes());
+        scatter_kernel<<<(unsigned)((n + 127) / 128), 128, perlin_smem_bytes()>>>(s->dev, d_in, n, seed, segment, d_out);
+        e = cudaMemcpy(h_out.data(), d_out, (size_t)n * sizeof(DevScatterOut), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_scatter_batch");
+    for (int64_t k = 0; k < n; ++k) {
+        const DevScatterOut& h = h_out[k];
+        rt_scatter_desc& o = out[k];
+        std::memset(&o, 0, sizeof(o));
+        o.scattered = h.scattered;
+        o.ray_out.origin[0] = h.ox; o.ray_out.origin[1] = h.oy; o.ray_out.origin[2] = h.oz;
+        o.ray_out.direction[0] = h.dx; o.ray_out.direction[1] = h.dy; o.ray_out.direction[2] = h.dz;
+        o.ray_out.time = h.time;
+        o.attenuation[0] = h.ar; o.attenuation[1] = h.ag; o.attenuation[2] = h.ab;
+        o.emitted[0] = h.er; o.emitted[1] = h.eg; o.emitted[2] = h.eb;
     }
     return RT_OK;
 }

@@ -19,6 +19,27 @@ def shard_samples(spp, rank, world_size, sample_begin=0):
     return begin, base + (1 if rank < extra else 0)
 
 
+def shard_samples_weighted(spp, weights, sample_begin=0):
+    """Contiguous split of [sample_begin, sample_begin + spp) in proportion to `weights` (one per rank: e.g. the paths/s
+    each GPU reached in a warm-up step). Returns [(begin, count)] for every rank; counts add up to spp exactly (largest
+    remainders get the leftover samples), so the union is the same set of (pixel, sample) paths a single GPU traces."""
+    if spp < 0 or not weights or any((not w == w) or w < 0 for w in weights):
+        raise ValueError("bad spp / weights")
+    total = float(sum(weights))
+    if total <= 0.0:
+        return [shard_samples(spp, r, len(weights), sample_begin) for r in range(len(weights))]
+    exact = [spp * w / total for w in weights]
+    counts = [int(x) for x in exact]
+    left = spp - sum(counts)
+    for r in sorted(range(len(weights)), key=lambda r: exact[r] - counts[r], reverse=True)[:left]:
+        counts[r] += 1
+    out, b = [], sample_begin
+    for c in counts:
+        out.append((b, c))
+        b += c
+    return out
+
+
 def reduce_to_root(framebuffer, group=None):
     """Sum the per-rank partial SUM framebuffers onto rank 0 (the only collective of the path)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -63,3 +63,21 @@ def test_two_rank_render_equals_single(rt, ob, tmp_path):
     want, _ = ob.render(s.desc, cam, 0, 9, seed=4, mode=0)
     assert np.all(got[..., 3] == 9)
     assert np.allclose(got[..., :3], want, rtol=1e-12, atol=1e-12)   # f64 partial sums in a different order
+
+
+def test_weighted_shards_cover_the_range_exactly():
+    """shard_samples_weighted: the proportional split bench.py uses at N > 1 (calibrated on a warm-up step)."""
+    from rust_tracing_b200.distributed import shard_samples_weighted
+    for spp, weights in ((10000, [1.0, 1.02, 0.97, 1.0, 0.95, 1.01, 1.0, 0.99]), (7, [3.0, 1.0]), (5, [1.0, 0.0, 3.0]), (0, [1.0, 2.0]),
+                         (13, [0.0, 0.0, 0.0]), (1, [0.2, 0.5, 0.3])):
+        parts = shard_samples_weighted(spp, weights, sample_begin=11)
+        assert len(parts) == len(weights)
+        assert parts[0][0] == 11 and all(parts[k + 1][0] == parts[k][0] + parts[k][1] for k in range(len(parts) - 1))
+        assert sum(c for _, c in parts) == spp and all(c >= 0 for _, c in parts)
+        tot = sum(weights)
+        if tot > 0:
+            assert all(abs(c - spp * w / tot) <= 1.0 for (_, c), w in zip(parts, weights))
+    with pytest.raises(ValueError):
+        shard_samples_weighted(-1, [1.0])
+    with pytest.raises(ValueError):
+        shard_samples_weighted(4, [1.0, float("nan")])
