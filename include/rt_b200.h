@@ -222,6 +222,9 @@ int rt_tex_solid(rt_builder* b, double r, double g, double bl);                 
 int rt_tex_checker(rt_builder* b, double scale, int even_tex, int odd_tex);               /* CheckerTexture::new texture.rs:44 */
 int rt_tex_image(rt_builder* b, int width, int height, const uint8_t* rgb8);              /* ImageTexture::new   texture.rs:76 (decoded) */
 int rt_tex_noise(rt_builder* b, double scale, uint64_t perlin_seed);                      /* NoiseTexture::new   texture.rs:100 */
+/* ... with the tables the host's own Perlin::new drew (perlin.rs:9-25): ranvec 256 x 3 doubles, perm_* 256 x int32 */
+int rt_tex_noise_tables(rt_builder* b, double scale, const double* ranvec, const int32_t* perm_x,
+                        const int32_t* perm_y, const int32_t* perm_z);
 
 int rt_mat_lambertian(rt_builder* b, int albedo_tex);                                     /* material.rs:22  */
 int rt_mat_metal(rt_builder* b, const double albedo[3], double fuzz);                     /* material.rs:49  */
@@ -234,11 +237,22 @@ int rt_hit_moving_sphere(rt_builder* b, const double center[3], const double tar
                          double radius, int mat);                                          /* .with_target       sphere.rs:34 */
 int rt_hit_quad(rt_builder* b, const double q[3], const double u[3], const double v[3], int mat); /* Quad::new  quad.rs:23 */
 int rt_hit_cube(rt_builder* b, const double a[3], const double bb[3], int mat);           /* Quad::cube         quad.rs:45 */
-int rt_hit_list(rt_builder* b, const int* ids, int n);                                    /* HittableList + add hittable.rs:56 */
+int rt_hit_list(rt_builder* b, const int* ids, int n);                                    /* HittableList + add hittable.rs:56
+                                                                                             (six quads that are what Quad::cube
+                                                                                             makes are recognised as a cube list) */
 int rt_hit_translate(rt_builder* b, int object, const double offset[3]);                  /* Translate::new     hittable.rs:87 */
 int rt_hit_rotate_y(rt_builder* b, int object, double angle_degrees);                     /* RotateY::new       hittable.rs:120 */
 int rt_hit_constant_medium(rt_builder* b, int boundary, double density, int albedo_tex);  /* ConstantMedium::new constant_medium.rs:21 */
 int rt_hit_bvh(rt_builder* b, const int* ids, int n);                                     /* BVHNode::new_from_objects bvh.rs:25 */
+/* The same hittable from a tree the HOST already built (the crate's own BVHNode, bvh.rs:12-19): nodes in pre-order, root
+ * first, left / right as indices into `nodes`, object = leaf hittable id or -1. The device walks exactly that tree. */
+int rt_hit_bvh_nodes(rt_builder* b, const rt_bvh_node_desc* nodes, int n);
+
+/* The same objects from their STORED state (a host that flattens objects it already built must hand over inv_scale,
+ * sin / cos and neg_inv_density bit for bit, not values that round-trip through 1/x, atan2 or -1/x). */
+int rt_tex_checker_inv(rt_builder* b, double inv_scale, int even_tex, int odd_tex);        /* texture.rs:38-42 */
+int rt_hit_rotate_y_sincos(rt_builder* b, int object, double sin_theta, double cos_theta); /* hittable.rs:113-118 */
+int rt_hit_constant_medium_nid(rt_builder* b, int boundary, double neg_inv_density, int albedo_tex); /* constant_medium.rs:14-18 */
 
 /* Fill *out with pointers into builder-owned memory (valid until rt_builder_destroy). */
 int rt_builder_finish(rt_builder* b, int world, rt_scene_desc* out);

@@ -146,6 +146,7 @@ PROTOTYPES = {
     "rt_tex_checker": (C.c_int, [vp, C.c_double, C.c_int, C.c_int]),
     "rt_tex_image": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "rt_tex_noise": (C.c_int, [vp, C.c_double, C.c_uint64]),
+    "rt_tex_noise_tables": (C.c_int, [vp, C.c_double, vp, vp, vp, vp]),
     "rt_mat_lambertian": (C.c_int, [vp, C.c_int]),
     "rt_mat_metal": (C.c_int, [vp, P(C.c_double), C.c_double]),
     "rt_mat_dielectric": (C.c_int, [vp, C.c_double]),
@@ -160,6 +161,10 @@ PROTOTYPES = {
     "rt_hit_rotate_y": (C.c_int, [vp, C.c_int, C.c_double]),
     "rt_hit_constant_medium": (C.c_int, [vp, C.c_int, C.c_double, C.c_int]),
     "rt_hit_bvh": (C.c_int, [vp, P(C.c_int), C.c_int]),
+    "rt_hit_bvh_nodes": (C.c_int, [vp, vp, C.c_int]),
+    "rt_tex_checker_inv": (C.c_int, [vp, C.c_double, C.c_int, C.c_int]),
+    "rt_hit_rotate_y_sincos": (C.c_int, [vp, C.c_int, C.c_double, C.c_double]),
+    "rt_hit_constant_medium_nid": (C.c_int, [vp, C.c_int, C.c_double, C.c_int]),
     "rt_builder_finish": (C.c_int, [vp, C.c_int, P(SceneDesc)]),
     "rt_camera_new": (C.c_int, [P(CameraSettingsC), P(CameraDesc)]),
     "rt_camera_settings_default": (None, [P(CameraSettingsC)]),

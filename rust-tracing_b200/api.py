@@ -90,6 +90,12 @@ class Scene:
     def NoiseTexture(self, scale, perlin_seed=3):
         return Handle(A.check(self._lib.rt_tex_noise(self._b, scale, int(perlin_seed))))
 
+    def NoiseTextureFromTables(self, scale, ranvec, perm_x, perm_y, perm_z):
+        """rt_tex_noise_tables: NoiseTexture whose Perlin tables the host drew itself (perlin.rs:16-25)."""
+        rv = np.ascontiguousarray(ranvec, dtype=np.float64).reshape(256, 3)
+        px, py, pz = (np.ascontiguousarray(p, dtype=np.int32).reshape(256) for p in (perm_x, perm_y, perm_z))
+        return Handle(A.check(self._lib.rt_tex_noise_tables(self._b, scale, rv.ctypes.data, px.ctypes.data, py.ctypes.data, pz.ctypes.data)))
+
     # ---- material.rs
     def Lambertian(self, albedo):
         return Handle(A.check(self._lib.rt_mat_lambertian(self._b, albedo)))
@@ -136,6 +142,15 @@ class Scene:
     def BVHNode(self, hlist):
         ids = (C.c_int * max(1, len(hlist.objects)))(*hlist.objects)
         return Handle(A.check(self._lib.rt_hit_bvh(self._b, ids, len(hlist.objects))))
+
+    def BVHFromNodes(self, nodes):
+        """rt_hit_bvh_nodes: a BVH the host built itself. `nodes`: pre-order sequence of (bbox[6], left, right, object)
+        with left / right indexing into the sequence (-1 for leaves) - what a Rust host reads off its own BVHNode."""
+        arr = (A.BvhNodeDesc * len(nodes))()
+        for k, (bbox, left, right, obj) in enumerate(nodes):
+            arr[k].bbox[:] = [float(x) for x in bbox]
+            arr[k].left, arr[k].right, arr[k].object, arr[k].axis = int(left), int(right), int(obj), -1
+        return Handle(A.check(self._lib.rt_hit_bvh_nodes(self._b, arr, len(nodes))))
 
     def finish(self, world):
         d = A.SceneDesc()

@@ -181,6 +181,13 @@ int rt_tex_solid(rt_builder* b, double r, double g, double bl) {
 }
 
 int rt_tex_checker(rt_builder* b, double scale, int even_tex, int odd_tex) {
+    return rt_tex_checker_inv(b, 1.0 / scale, even_tex, odd_tex);  // texture.rs:46
+}
+
+// The *_inv / *_sincos / *_nid constructors take the object's STORED state instead of the constructor's argument: a host
+// that flattens objects it already built must hand over inv_scale, sin / cos, neg_inv_density bit for bit,
+// not values that round-trip through 1/x, atan2 or -1/x.
+int rt_tex_checker_inv(rt_builder* b, double inv_scale, int even_tex, int odd_tex) {
     if (!b) return fail(RT_ERR_INVALID_ARGUMENT, "rt_tex_checker: builder is null");
     if (!valid_id(even_tex, b->textures.size()) || !valid_id(odd_tex, b->textures.size()))
         return fail(RT_ERR_OUT_OF_RANGE, "rt_tex_checker: unknown texture id");
@@ -188,7 +195,7 @@ int rt_tex_checker(rt_builder* b, double scale, int even_tex, int odd_tex) {
     t.kind = RT_TEX_CHECKER;
     t.a = even_tex;
     t.b = odd_tex;
-    t.scale = 1.0 / scale;  // texture.rs:46
+    t.scale = inv_scale;
     b->textures.push_back(t);
     return (int)b->textures.size() - 1;
 }
@@ -215,6 +222,29 @@ int rt_tex_noise(rt_builder* b, double scale, uint64_t perlin_seed) {
     if (!b) return fail(RT_ERR_INVALID_ARGUMENT, "rt_tex_noise: builder is null");
     b->perlins.emplace_back();
     perlin_new(perlin_seed, &b->perlins.back());
+    rt_texture_desc t{};
+    t.kind = RT_TEX_NOISE;
+    t.a = (int)b->perlins.size() - 1;
+    t.b = -1;
+    t.scale = scale;
+    b->textures.push_back(t);
+    return (int)b->textures.size() - 1;
+}
+
+// NoiseTexture with the tables the HOST drew (the crate's Perlin::new uses its unseeded thread_rng, perlin.rs:16-25): a
+// drop-in must shade with exactly those. ranvec: 256 x 3, perm_*: 256 entries in [0, 256).
+int rt_tex_noise_tables(rt_builder* b, double scale, const double* ranvec, const int32_t* perm_x, const int32_t* perm_y,
+                        const int32_t* perm_z) {
+    if (!b || !ranvec || !perm_x || !perm_y || !perm_z) return fail(RT_ERR_INVALID_ARGUMENT, "rt_tex_noise_tables: null argument");
+    for (int k = 0; k < 256; ++k)
+        if ((uint32_t)perm_x[k] > 255u || (uint32_t)perm_y[k] > 255u || (uint32_t)perm_z[k] > 255u)
+            return fail(RT_ERR_OUT_OF_RANGE, "rt_tex_noise_tables: permutation entries must lie in [0, 256)");
+    b->perlins.emplace_back();
+    rt_perlin_desc& p = b->perlins.back();
+    for (int k = 0; k < 256; ++k) {
+        for (int c = 0; c < 3; ++c) p.ranvec[k][c] = ranvec[3 * k + c];
+        p.perm_x[k] = perm_x[k]; p.perm_y[k] = perm_y[k]; p.perm_z[k] = perm_z[k];
+    }
     rt_texture_desc t{};
     t.kind = RT_TEX_NOISE;
     t.a = (int)b->perlins.size() - 1;
@@ -333,6 +363,31 @@ int rt_hit_list(rt_builder* b, const int* ids, int n) {
         bbox_union(h.bbox, b->hittables[ids[i]].bbox, u);
         std::memcpy(h.bbox, u, sizeof(u));
     }
+    // A host that flattens its own objects cannot say "this list came from Quad::cube": recognise it. Six
+    // consecutive quads of one material that are, bit for bit, what quad.rs:45-93 makes of some (min, max) pair.
+    if (n == 6) {
+        bool cube = true;
+        for (int k = 0; k < 6 && cube; ++k) {
+            const rt_hittable_desc& q = b->hittables[ids[k]];
+            cube = ids[k] == ids[0] + k && q.kind == RT_HIT_QUAD && q.mat == b->hittables[ids[0]].mat;
+        }
+        if (cube) {
+            const rt_hittable_desc* q = &b->hittables[ids[0]];
+            const double mn[3] = {q[3].v0[0], q[3].v0[1], q[3].v0[2]}, mx[3] = {q[1].v0[0], q[4].v0[1], q[0].v0[2]};
+            const double dx[3] = {mx[0] - mn[0], 0.0, 0.0}, dy[3] = {0.0, mx[1] - mn[1], 0.0}, dz[3] = {0.0, 0.0, mx[2] - mn[2]};
+            const double ndx[3] = {-dx[0], -0.0, -0.0}, ndz[3] = {-0.0, -0.0, -dz[2]};
+            const double q0[3] = {mn[0], mn[1], mx[2]}, q1[3] = {mx[0], mn[1], mx[2]}, q2[3] = {mx[0], mn[1], mn[2]},
+                         q3[3] = {mn[0], mn[1], mn[2]}, q4[3] = {mn[0], mx[1], mx[2]}, q5[3] = {mn[0], mn[1], mn[2]};
+            const double* want[6][3] = {{q0, dx, dy}, {q1, ndz, dy}, {q2, ndx, dy}, {q3, dz, dy}, {q4, dx, ndz}, {q5, dx, dz}};
+            for (int k = 0; k < 6 && cube; ++k)
+                for (int c = 0; c < 3 && cube; ++c)   // == treats -0.0 and 0.0 alike, as the quads' arithmetic does
+                    cube = q[k].v0[c] == want[k][0][c] && q[k].v1[c] == want[k][1][c] && q[k].v2[c] == want[k][2][c];
+            if (cube) {
+                h.flags |= RT_FLAG_CUBE_LIST;
+                for (int k = 0; k < 3; ++k) { h.v0[k] = mn[k]; h.v1[k] = mx[k]; }
+            }
+        }
+    }
     b->hittables.push_back(h);
     return (int)b->hittables.size() - 1;
 }
@@ -379,13 +434,16 @@ int rt_hit_translate(rt_builder* b, int object, const double offset[3]) {
 }
 
 int rt_hit_rotate_y(rt_builder* b, int object, double angle) {
+    const double theta = angle * kPi / 180.0;  // common.rs:6-8
+    return rt_hit_rotate_y_sincos(b, object, std::sin(theta), std::cos(theta));
+}
+
+int rt_hit_rotate_y_sincos(rt_builder* b, int object, double sin_theta, double cos_theta) {
     if (!b) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_rotate_y: builder is null");
     if (!valid_id(object, b->hittables.size())) return fail(RT_ERR_OUT_OF_RANGE, "rt_hit_rotate_y: unknown hittable id");
     rt_hittable_desc h = blank_hittable(RT_HIT_ROTATE_Y);
     h.child = object;
     // hittable.rs:120-157
-    const double theta = angle * kPi / 180.0;  // common.rs:6-8
-    const double sin_theta = std::sin(theta), cos_theta = std::cos(theta);
     h.s0 = sin_theta;
     h.s1 = cos_theta;
     const double* cb = b->hittables[object].bbox;
@@ -409,12 +467,16 @@ int rt_hit_rotate_y(rt_builder* b, int object, double angle) {
 }
 
 int rt_hit_constant_medium(rt_builder* b, int boundary, double density, int tex) {
+    return rt_hit_constant_medium_nid(b, boundary, -1.0 / density, tex);   // constant_medium.rs:24
+}
+
+int rt_hit_constant_medium_nid(rt_builder* b, int boundary, double neg_inv_density, int tex) {
     if (!b) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_constant_medium: builder is null");
     if (!valid_id(boundary, b->hittables.size())) return fail(RT_ERR_OUT_OF_RANGE, "rt_hit_constant_medium: unknown hittable id");
     if (!valid_id(tex, b->textures.size())) return fail(RT_ERR_OUT_OF_RANGE, "rt_hit_constant_medium: unknown texture id");
     rt_hittable_desc h = blank_hittable(RT_HIT_CONSTANT_MEDIUM);
     h.child = boundary;
-    h.s0 = -1.0 / density;                 // constant_medium.rs:24
+    h.s0 = neg_inv_density;
     h.mat = rt_mat_isotropic(b, tex);      // constant_medium.rs:25
     std::memcpy(h.bbox, b->hittables[boundary].bbox, sizeof(h.bbox));  // constant_medium.rs:73-75
     b->hittables.push_back(h);
@@ -433,6 +495,43 @@ int rt_hit_bvh(rt_builder* b, const int* ids, int n) {
     h.child = root;
     h.count = (int32_t)b->bvh_nodes.size() - first;
     std::memcpy(h.bbox, b->bvh_nodes[root].bbox, sizeof(h.bbox));  // bvh.rs:120-122
+    b->hittables.push_back(h);
+    return (int)b->hittables.size() - 1;
+}
+
+// A BVH the HOST built (the crate's own BVHNode::node_from_list run, bvh.rs:31-66: its thread_rng axis draws, its sort):
+// `nodes` in pre-order, nodes[0] the root, left / right as indices into `nodes` (children after their parent),
+// object = the leaf's hittable id or -1, bbox = the node's own (bvh.rs:64-66). The device then walks exactly the tree
+// the Rust side holds; rt_hit_bvh above builds one with the same rule from a seeded stream instead.
+int rt_hit_bvh_nodes(rt_builder* b, const rt_bvh_node_desc* nodes, int n) {
+    if (!b || !nodes) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_bvh_nodes: null argument");
+    if (n <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_bvh_nodes: a BVH needs at least one node");
+    std::vector<char> seen((size_t)n, 0);
+    int leaves = 0;
+    for (int i = 0; i < n; ++i) {
+        const rt_bvh_node_desc& nd = nodes[i];
+        if (nd.object >= 0) {
+            if (!valid_id(nd.object, b->hittables.size())) return fail(RT_ERR_OUT_OF_RANGE, "rt_hit_bvh_nodes: leaf names an unknown hittable");
+            ++leaves;
+        } else {
+            if (nd.left <= i || nd.right <= i || nd.left >= n || nd.right >= n || nd.left == nd.right)
+                return fail(RT_ERR_OUT_OF_RANGE, "rt_hit_bvh_nodes: children must follow their parent (pre-order)");
+            if (seen[nd.left]++ || seen[nd.right]++) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_bvh_nodes: a node has two parents");
+        }
+    }
+    for (int i = 1; i < n; ++i) if (!seen[i]) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_bvh_nodes: unreachable node");
+    if (n != 2 * leaves - 1) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_bvh_nodes: not a full binary tree");
+    const int32_t first = (int32_t)b->bvh_nodes.size();
+    for (int i = 0; i < n; ++i) {
+        rt_bvh_node_desc nd = nodes[i];
+        if (nd.object >= 0) { nd.left = -1; nd.right = -1; }
+        else { nd.left += first; nd.right += first; }
+        b->bvh_nodes.push_back(nd);
+    }
+    rt_hittable_desc h = blank_hittable(RT_HIT_BVH);
+    h.child = first;
+    h.count = n;
+    std::memcpy(h.bbox, nodes[0].bbox, sizeof(h.bbox));  // bvh.rs:120-122
     b->hittables.push_back(h);
     return (int)b->hittables.size() - 1;
 }

@@ -182,3 +182,92 @@ def test_earth_required(rt):
         s = rt._abi.SceneRequest(); s.scene = 2
         raw, d, cs = C.c_void_p(), rt._abi.SceneDesc(), rt.CameraSettings()
         rt._abi.check(rt._abi.lib().rt_scene_builtin(C.byref(s), C.byref(raw), C.byref(d), C.byref(cs)))
+
+
+def test_bvh_imported_from_host_nodes_equals_the_built_one(rt, ob):
+    """rt_hit_bvh_nodes: the drop-in's Rust host hands over the BVH it already built (bvh.rs:12-19). Re-importing the
+    nodes of a tree built here must give the same description, the same device stream and the same hits."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+
+    def objects(s):
+        m = s.Lambertian(s.SolidColor(0.5, 0.5, 0.5))
+        l = rt.HittableList()
+        for _ in range(37):
+            c = rng.uniform(-10, 10, 3)
+            l.add(s.Sphere(tuple(c), float(rng.uniform(0.3, 1.5)), m))
+        l.add(s.Quad((-3, -3, 4), (6, 0, 0), (0, 6, 0), m))
+        return l
+    state = rng.bit_generator.state
+    a = rt.Scene(bvh_seed=9)
+    a.finish(a.BVHNode(objects(a)))
+    d = a.desc
+    root = d.hittables[d.world].child
+    nodes = []
+    for k in range(d.hittables[d.world].count):
+        nd = d.bvh_nodes[root + k]
+        nodes.append((list(nd.bbox), nd.left - root if nd.left >= 0 else -1, nd.right - root if nd.right >= 0 else -1, nd.object))
+    rng.bit_generator.state = state
+    b = rt.Scene(bvh_seed=12345)           # the seed plays no role: no tree is built
+    objects(b)
+    b.finish(b.BVHFromNodes(nodes))
+    wa, wb = rt.scene_ops(a)["words"], rt.scene_ops(b)["words"]
+    assert wa.shape == wb.shape and np.array_equal(wa.view(np.uint32), wb.view(np.uint32))
+    rays = np.zeros(4096, dtype=rt._abi.ray_dtype())
+    rays["origin"] = rng.uniform(-12, 12, (4096, 3))
+    rays["direction"] = rng.normal(size=(4096, 3))
+    ha, hb = ob.hit_batch(a.desc, rays), ob.hit_batch(b.desc, rays)
+    assert np.array_equal(ha["hit"], hb["hit"]) and np.array_equal(ha["prim_id"], hb["prim_id"]) and np.array_equal(ha["t"], hb["t"])
+    # malformed trees are refused
+    lib = rt._abi.lib()
+    bad = (rt._abi.BvhNodeDesc * 3)()
+    bad[0].left, bad[0].right, bad[0].object = 1, 1, -1
+    bad[1].object = bad[2].object = 0
+    assert lib.rt_hit_bvh_nodes(b._b, bad, 3) < 0
+    bad[0].left, bad[0].right = 1, 2
+    bad[2].object = 10 ** 6
+    assert lib.rt_hit_bvh_nodes(b._b, bad, 3) == rt._abi.RT_ERR_OUT_OF_RANGE
+    assert lib.rt_hit_bvh_nodes(b._b, bad, 2) < 0
+
+
+def test_flattened_cube_lists_and_host_perlin_tables(rt):
+    """What a host that flattens its own objects relies on (INTEGRATION.md): a HittableList of the six quads Quad::cube makes
+    is recognised as a cube (one slab primitive on the device) without being told, a list that merely looks similar is not,
+    and a NoiseTexture can carry the Perlin tables the host drew."""
+    a = rt.Scene()
+    m = a.Lambertian(a.SolidColor(0.5, 0.5, 0.5))
+    a.finish(a.cube((1, 2, 3), (4, 6, 5), m))
+    cube = a.desc.hittables[a.desc.world]
+    quads = [a.desc.hittables[a.desc.list_items[cube.child + k]] for k in range(6)]
+    b = rt.Scene()
+    mb = b.Lambertian(b.SolidColor(0.5, 0.5, 0.5))
+    l = rt.HittableList()
+    for q in quads:
+        l.add(b.Quad(tuple(q.v0), tuple(q.v1), tuple(q.v2), mb))
+    b.finish(b.List(l))
+    got = b.desc.hittables[b.desc.world]
+    assert got.flags & rt._abi.RT_FLAG_CUBE_LIST and tuple(got.v0) == (1, 2, 3) and tuple(got.v1) == (4, 6, 5)
+    assert rt.scene_layout(b)["n_box"] == 1 and rt.scene_layout(b)["n_quad"] == 0
+    c = rt.Scene()
+    mc = c.Lambertian(c.SolidColor(0.5, 0.5, 0.5))
+    l = rt.HittableList()
+    for k, q in enumerate(quads):
+        u = tuple(q.v1) if k != 2 else (q.v1[0] * 0.5, q.v1[1], q.v1[2])        # one face shrunk: not a cube
+        l.add(c.Quad(tuple(q.v0), u, tuple(q.v2), mc))
+    c.finish(c.List(l))
+    assert not (c.desc.hittables[c.desc.world].flags & rt._abi.RT_FLAG_CUBE_LIST)
+    assert rt.scene_layout(c)["n_box"] == 0 and rt.scene_layout(c)["n_quad"] == 6
+    # host-drawn Perlin tables end up in the description untouched
+    s = rt.Scene()
+    ref = s.NoiseTexture(4.0, perlin_seed=3)
+    p = s.desc if s.desc else None
+    s.finish(s.Sphere((0, 0, 0), 1.0, s.Lambertian(ref)))
+    t0 = s.desc.perlins[0]
+    rv = np.array([[t0.ranvec[k][c] for c in range(3)] for k in range(256)])
+    px, py, pz = (np.array(t0.perm_x[:]), np.array(t0.perm_y[:]), np.array(t0.perm_z[:]))
+    s2 = rt.Scene()
+    s2.finish(s2.Sphere((0, 0, 0), 1.0, s2.Lambertian(s2.NoiseTextureFromTables(4.0, rv, px, py, pz))))
+    t1 = s2.desc.perlins[0]
+    assert bytes(t0) == bytes(t1)
+    with pytest.raises(rt._abi.RtError):
+        s2.NoiseTextureFromTables(4.0, rv, px + 300, py, pz)
