@@ -290,6 +290,43 @@ int rt_device_info(rt_context* ctx, int* sm_count, int* sm_clock_khz, size_t* to
 int rt_scene_upload(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out);
 void rt_scene_destroy(rt_scene* scene);
 
+/* Host work moved to the GPU, results identical to the host forms:
+ * rt_hit_bvh_device   rt_hit_bvh (BVHNode::node_from_list, bvh.rs:31-66) with the per-level sorting on the device - same
+ *                     seeded axis stream, same node array, bit for bit;
+ * rt_bvh_build_device the build itself on caller-supplied boxes (n x 6 doubles: x.min x.max y.min ...) and axis draws
+ *                     (rt_bvh_axis_draws(n) of them, in the order node_from_list makes them); nodes_out receives 2n - 1
+ *                     nodes in pre-order whose leaf `object` is the index into the input; returns the node count;
+ * rt_jpeg_decode      ImageTexture::new's decode (texture.rs:76-80): JPEG bytes -> tightly packed RGB8 in host memory, ready
+ *                     for rt_tex_image; host_rgb8 == NULL only queries the size. The entropy (Huffman) decode is one serial
+ *                     bit stream and runs on the host; dequantisation, the inverse DCT, chroma upsampling and YCbCr -> RGB
+ *                     run on the device with libjpeg's integer arithmetic (islow IDCT, fancy upsampling), so the bytes
+ *                     equal libjpeg-turbo's / PIL's - the decode every other input of this library and of the oracle came
+ *                     from. Baseline Huffman streams, 8 bit, grey or three components at 4:4:4 / 4:2:2 / 4:2:0; anything
+ *                     else is RT_ERR_UNSUPPORTED;
+ * rt_jpeg_entropy_decode  the host half alone (no GPU): frame geometry, quantisation tables and, when coef != NULL, the
+ *                     quantised coefficients (int16, natural order, 64 per block, blocks row-major per component plane);
+ * rt_jpeg_decode_nvjpeg   the same contract through NVIDIA's nvJPEG (libnvjpeg.so.12 is loaded on first use,
+ *                     RT_ERR_UNSUPPORTED without it). A library decoder with its own IDCT and plain chroma replication:
+ *                     NOT byte-identical to libjpeg; tests/test_gpu_jpeg.py states the measured distance. */
+typedef struct rt_jpeg_info {
+    int32_t width, height, components;
+    int32_t h_samp[3], v_samp[3];
+    int32_t blocks_w[3], blocks_h[3];     /* blocks stored per component (padded to whole MCUs) */
+    int32_t adobe_rgb;                    /* Adobe APP14 transform 0: components are R, G, B */
+    uint16_t quant[3][64];                /* per component, natural order */
+    int64_t coef_offset[3];               /* first coefficient of the component, in int16 units */
+    int64_t coef_count;
+} rt_jpeg_info;
+int rt_hit_bvh_device(rt_builder* b, rt_context* ctx, const int* ids, int n);
+int rt_bvh_axis_draws(int n);
+int rt_bvh_build_device(rt_context* ctx, const double* bboxes, int n, const int32_t* axes, rt_bvh_node_desc* nodes_out,
+                        int32_t* order_out);
+int rt_jpeg_decode(rt_context* ctx, const uint8_t* jpeg, size_t n_bytes, int* width, int* height, uint8_t* host_rgb8,
+                   size_t capacity);
+int rt_jpeg_entropy_decode(const uint8_t* jpeg, size_t n_bytes, rt_jpeg_info* info, int16_t* coef, size_t capacity);
+int rt_jpeg_decode_nvjpeg(rt_context* ctx, const uint8_t* jpeg, size_t n_bytes, int* width, int* height, uint8_t* host_rgb8,
+                          size_t capacity);
+
 /* Switches of the flattening, for tests and A/B runs (0 = the product's layout). Every combination renders the same
  * image: they only change how the device walks the scene. */
 #define RT_LAYOUT_NO_PRUNE 1u           /* keep every cull box of the reference's BVH (no prune_stream) */

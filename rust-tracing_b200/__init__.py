@@ -6,8 +6,8 @@ Import name: `rust_tracing_b200` (the directory is `rust-tracing_b200/`; see ../
 """
 from . import _abi
 from .api import (Camera, CameraSettings, Context, DeviceScene, Handle, HittableList, Scene, SCENE_NAMES,
-                  builtin_scene, color_to_rgb8, default_context, layout_flags, load_earth, render, render_multi, scene_layout, scene_ops,
+                  builtin_scene, color_to_rgb8, default_context, jpeg_entropy_decode, layout_flags, load_earth, render, render_multi, scene_layout, scene_ops,
                   synthetic_earth)
 
 __all__ = ["Camera", "CameraSettings", "Context", "DeviceScene", "Handle", "HittableList", "Scene", "SCENE_NAMES",
-           "builtin_scene", "color_to_rgb8", "default_context", "layout_flags", "load_earth", "render", "render_multi", "scene_layout", "scene_ops", "synthetic_earth", "_abi"]
+           "builtin_scene", "color_to_rgb8", "default_context", "jpeg_entropy_decode", "layout_flags", "load_earth", "render", "render_multi", "scene_layout", "scene_ops", "synthetic_earth", "_abi"]

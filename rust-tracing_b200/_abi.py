@@ -57,6 +57,13 @@ class PerlinDesc(C.Structure):
                 ("perm_y", C.c_int32 * 256), ("perm_z", C.c_int32 * 256)]
 
 
+class JpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32),
+                ("h_samp", C.c_int32 * 3), ("v_samp", C.c_int32 * 3), ("blocks_w", C.c_int32 * 3), ("blocks_h", C.c_int32 * 3),
+                ("adobe_rgb", C.c_int32), ("quant", (C.c_uint16 * 64) * 3), ("coef_offset", C.c_int64 * 3),
+                ("coef_count", C.c_int64)]
+
+
 class ImageDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("rgb8", C.POINTER(C.c_uint8))]
 
@@ -174,6 +181,12 @@ PROTOTYPES = {
     "rt_device_info": (C.c_int, [vp, P(C.c_int), P(C.c_int), P(C.c_size_t)]),
     "rt_scene_upload": (C.c_int, [vp, P(SceneDesc), P(vp)]),
     "rt_scene_destroy": (None, [vp]),
+    "rt_hit_bvh_device": (C.c_int, [vp, vp, P(C.c_int), C.c_int]),
+    "rt_bvh_axis_draws": (C.c_int, [C.c_int]),
+    "rt_bvh_build_device": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
+    "rt_jpeg_decode": (C.c_int, [vp, vp, C.c_size_t, P(C.c_int), P(C.c_int), vp, C.c_size_t]),
+    "rt_jpeg_decode_nvjpeg": (C.c_int, [vp, vp, C.c_size_t, P(C.c_int), P(C.c_int), vp, C.c_size_t]),
+    "rt_jpeg_entropy_decode": (C.c_int, [vp, C.c_size_t, P(JpegInfo), vp, C.c_size_t]),
     "rt_scene_upload_ex": (C.c_int, [vp, P(SceneDesc), C.c_uint32, P(vp)]),
     "rt_scene_layout": (C.c_int, [P(SceneDesc), C.c_uint32, P(LayoutInfo)]),
     "rt_scene_ops_export": (C.c_int, [P(SceneDesc), C.c_uint32, P(C.c_float), C.c_int64, P(C.c_int64), P(C.c_int32), P(C.c_int32),

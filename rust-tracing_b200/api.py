@@ -143,6 +143,11 @@ class Scene:
         ids = (C.c_int * max(1, len(hlist.objects)))(*hlist.objects)
         return Handle(A.check(self._lib.rt_hit_bvh(self._b, ids, len(hlist.objects))))
 
+    def BVHNodeOnDevice(self, ctx, hlist):
+        """rt_hit_bvh_device: BVHNode::new with the sorting on the GPU; the same node array as BVHNode(hlist)."""
+        ids = (C.c_int * max(1, len(hlist.objects)))(*hlist.objects)
+        return Handle(A.check(self._lib.rt_hit_bvh_device(self._b, ctx._h, ids, len(hlist.objects))))
+
     def BVHFromNodes(self, nodes):
         """rt_hit_bvh_nodes: a BVH the host built itself. `nodes`: pre-order sequence of (bbox[6], left, right, object)
         with left / right indexing into the sequence (-1 for leaves) - what a Rust host reads off its own BVHNode."""
@@ -222,6 +227,17 @@ def synthetic_earth(width=6400, height=3200, seed=11):
 
 
 _REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def jpeg_entropy_decode(data):
+    """rt_jpeg_entropy_decode (host only): -> (JpegInfo, int16 coefficients)."""
+    lib = A.lib()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    info = A.JpegInfo()
+    A.check(lib.rt_jpeg_entropy_decode(buf.ctypes.data, len(buf), C.byref(info), None, 0))
+    coef = np.empty(info.coef_count, dtype=np.int16)
+    A.check(lib.rt_jpeg_entropy_decode(buf.ctypes.data, len(buf), C.byref(info), coef.ctypes.data, coef.size))
+    return info, coef
 
 
 def load_earth(path=None):
@@ -421,6 +437,17 @@ class Context:
         out = np.zeros(len(rays), dtype=A.scatter_dtype())
         A.check(self._lib.rt_scatter_batch(self._h, dscene._h, rays.ctypes.data, hits.ctypes.data, len(rays), seed,
                                            pixel.ctypes.data, sample.ctypes.data, int(segment), out.ctypes.data))
+        return out
+
+    def jpeg_decode(self, data, backend="own"):
+        """rt_jpeg_decode (host Huffman + this library's kernels, bytes equal to libjpeg-turbo's) or, backend="nvjpeg",
+        rt_jpeg_decode_nvjpeg: JPEG bytes -> uint8 (H, W, 3)."""
+        fn = self._lib.rt_jpeg_decode if backend == "own" else self._lib.rt_jpeg_decode_nvjpeg
+        buf = np.frombuffer(data, dtype=np.uint8)
+        w, h = C.c_int(), C.c_int()
+        A.check(fn(self._h, buf.ctypes.data, len(buf), C.byref(w), C.byref(h), None, 0))
+        out = np.empty((h.value, w.value, 3), dtype=np.uint8)
+        A.check(fn(self._h, buf.ctypes.data, len(buf), C.byref(w), C.byref(h), out.ctypes.data, out.nbytes))
         return out
 
     def bvh_export(self, dscene, bvh_hittable, capacity=1 << 20):

@@ -14,6 +14,7 @@ OUT = os.path.join(CSRC, "librt_b200.so")
 SOURCES = [
     os.path.join(CSRC, "host", "scene_builder.cpp"),
     os.path.join(CSRC, "host", "scenes.cpp"),
+    os.path.join(CSRC, "host", "jpeg_entropy.cpp"),
     os.path.join(CSRC, "device", "scene_compile.cpp"),
     os.path.join(CSRC, "device", "rt_cuda.cu"),
 ]
@@ -23,6 +24,9 @@ DEPS = SOURCES + [
     os.path.join(CSRC, "device", "dev_scene.h"),
     os.path.join(CSRC, "device", "rt_kernels.cuh"),
     os.path.join(CSRC, "device", "render_mk.cuh"),
+    os.path.join(CSRC, "device", "bvh_build.cuh"),
+    os.path.join(CSRC, "device", "jpeg_kernels.cuh"),
+    os.path.join(CSRC, "host", "jpeg_entropy.h"),
     os.path.join(HERE, "..", "include", "rt_b200.h"),
     os.path.join(HERE, "..", "include", "rt_b200.hpp"),
 ]

@@ -89,7 +89,7 @@ __device__ __noinline__ uint32_t shade_phase(uint32_t link, unsigned* cnt) {
     uint8_t* sh_perm = reinterpret_cast<uint8_t*>(sh_vec + np * 256);
     float* cold = reinterpret_cast<float*>(sh_perm + np * 768);
     int* pool = reinterpret_cast<int*>(cold + kColdFields * kRenderThreads) + (threadIdx.x >> 5) * kPoolFields;
-    const PerlinShared P{sh_vec, sh_perm};
+    const PerlinShared P{sh_vec, sh_perm, min(S.n_perlin, kMaxPerlinShared)};
     Ops ops;
     set_ops_base(ops, S.ops);
     const int tid = threadIdx.x;

@@ -110,7 +110,7 @@ __global__ void texture_kernel(DevScene S, int tex, const float* uvp, int64_t n,
     float4* sh_vec = dyn_smem;
     uint8_t* sh_perm = reinterpret_cast<uint8_t*>(dyn_smem + kMaxPerlinShared * 256);
     stage_perlin(S, sh_vec, sh_perm);
-    PerlinShared P{sh_vec, sh_perm};
+    PerlinShared P{sh_vec, sh_perm, min(S.n_perlin, kMaxPerlinShared)};
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float3 c = texture_value(S, P, tex, f3(uvp[k * 5 + 2], uvp[k * 5 + 3], uvp[k * 5 + 4]), uvp[k * 5], uvp[k * 5 + 1], false,
@@ -136,7 +136,7 @@ __global__ void scatter_kernel(DevScene S, const DevScatterIn* in, int64_t n, ui
     float4* sh_vec = dyn_smem;
     uint8_t* sh_perm = reinterpret_cast<uint8_t*>(dyn_smem + min(S.n_perlin, kMaxPerlinShared) * 256);
     stage_perlin(S, sh_vec, sh_perm);
-    PerlinShared P{sh_vec, sh_perm};
+    PerlinShared P{sh_vec, sh_perm, min(S.n_perlin, kMaxPerlinShared)};
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const DevScatterIn r = in[k];
@@ -325,7 +325,147 @@ static cudaError_t staged_upload(rt_context* c, void* dst, const void* src, size
     return cudaSuccess;
 }
 
+#include "bvh_build.cuh"
+#include "jpeg_kernels.cuh"
+#include "../host/jpeg_entropy.h"
+
+// ---- nvJPEG through dlopen (like NCCL: a host that hands over decoded pixels needs no libnvjpeg)
+#include <nvjpeg.h>
+namespace {
+struct NvjpegApi {
+    void* handle = nullptr;
+    bool tried = false;
+    nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t*) = nullptr;
+    nvjpegStatus_t (*Destroy)(nvjpegHandle_t) = nullptr;
+    nvjpegStatus_t (*JpegStateCreate)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
+    nvjpegStatus_t (*JpegStateDestroy)(nvjpegJpegState_t) = nullptr;
+    nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
+    nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t, nvjpegImage_t*, cudaStream_t) = nullptr;
+};
+NvjpegApi g_nvjpeg;
+int load_nvjpeg() {
+    if (g_nvjpeg.Decode) return RT_OK;
+    if (!g_nvjpeg.tried) {
+        g_nvjpeg.tried = true;
+        for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so"}) {
+            g_nvjpeg.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (g_nvjpeg.handle) break;
+        }
+        if (g_nvjpeg.handle) {
+            void* h = g_nvjpeg.handle;
+            g_nvjpeg.CreateSimple = reinterpret_cast<decltype(g_nvjpeg.CreateSimple)>(dlsym(h, "nvjpegCreateSimple"));
+            g_nvjpeg.Destroy = reinterpret_cast<decltype(g_nvjpeg.Destroy)>(dlsym(h, "nvjpegDestroy"));
+            g_nvjpeg.JpegStateCreate = reinterpret_cast<decltype(g_nvjpeg.JpegStateCreate)>(dlsym(h, "nvjpegJpegStateCreate"));
+            g_nvjpeg.JpegStateDestroy = reinterpret_cast<decltype(g_nvjpeg.JpegStateDestroy)>(dlsym(h, "nvjpegJpegStateDestroy"));
+            g_nvjpeg.GetImageInfo = reinterpret_cast<decltype(g_nvjpeg.GetImageInfo)>(dlsym(h, "nvjpegGetImageInfo"));
+            g_nvjpeg.Decode = reinterpret_cast<decltype(g_nvjpeg.Decode)>(dlsym(h, "nvjpegDecode"));
+        }
+    }
+    if (!g_nvjpeg.CreateSimple || !g_nvjpeg.Destroy || !g_nvjpeg.JpegStateCreate || !g_nvjpeg.JpegStateDestroy || !g_nvjpeg.GetImageInfo || !g_nvjpeg.Decode)
+        return fail(RT_ERR_UNSUPPORTED, "rt_jpeg_decode: libnvjpeg.so.12 could not be loaded");
+    return RT_OK;
+}
+}  // namespace
+
 extern "C" {
+
+// ImageTexture::new's decode (texture.rs:76-80): JPEG bytes -> tightly packed RGB8, row 0 = top, in host memory (then
+// rt_tex_image as usual). width / height are always filled in; host_rgb8 may be NULL to query them. Host: markers and the
+// Huffman bit stream (jpeg_entropy.cpp); device: everything per block and per pixel (jpeg_kernels.cuh).
+int rt_jpeg_decode(rt_context* c, const uint8_t* jpeg, size_t n_bytes, int* width, int* height, uint8_t* host_rgb8, size_t capacity) {
+    if (!c || !jpeg || !width || !height || n_bytes == 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_jpeg_decode: null argument");
+    rt_host::JpegFrame f;
+    std::string err;
+    int rc = rt_host::jpeg_entropy_decode(jpeg, n_bytes, &f, nullptr, 0, &err);
+    if (rc < 0) return fail(rc, "rt_jpeg_decode: " + err);
+    *width = f.width;
+    *height = f.height;
+    if (!host_rgb8) return RT_OK;
+    const size_t need = (size_t)f.width * (size_t)f.height * 3;
+    if (capacity < need) return fail(RT_ERR_OUT_OF_RANGE, "rt_jpeg_decode: capacity too small");
+    int mode = 0;
+    if (f.ncomp == 3) {
+        const rt_host::JpegComponent &Y = f.comp[0], &B = f.comp[1], &R = f.comp[2];
+        if (B.h != R.h || B.v != R.v || B.h != 1 || B.v != 1 || Y.h != f.hmax || Y.v != f.vmax)
+            return fail(RT_ERR_UNSUPPORTED, "rt_jpeg_decode: chroma layouts other than 4:4:4, 4:2:2 and 4:2:0 are not supported");
+        if (Y.h == 1 && Y.v == 1) mode = 1;
+        else if (Y.h == 2 && Y.v == 1) mode = 2;
+        else if (Y.h == 2 && Y.v == 2) mode = 3;
+        else return fail(RT_ERR_UNSUPPORTED, "rt_jpeg_decode: chroma layouts other than 4:4:4, 4:2:2 and 4:2:0 are not supported");
+    }
+    CU(cudaSetDevice(c->device));
+    // pinned coefficients (the Huffman decoder writes them where the DMA engine reads them), one device block for
+    // coefficients + sample planes + RGB
+    struct Guard { int16_t* h = nullptr; unsigned char* d = nullptr; ~Guard() { if (h) cudaFreeHost(h); if (d) cudaFree(d); } } g;
+    CU(cudaMallocHost(&g.h, f.coef_count * sizeof(int16_t)));
+    rc = rt_host::jpeg_entropy_decode(jpeg, n_bytes, &f, g.h, f.coef_count, &err);
+    if (rc < 0) return fail(rc, "rt_jpeg_decode: " + err);
+    size_t plane_off[3], off = (f.coef_count * sizeof(int16_t) + 255) & ~(size_t)255;
+    for (int k = 0; k < f.ncomp; ++k) {
+        plane_off[k] = off;
+        off += ((size_t)f.comp[k].blocks_w * 8 * f.comp[k].blocks_h * 8 + 255) & ~(size_t)255;
+    }
+    const size_t rgb_off = off;
+    off += need;
+    CU(cudaMalloc(&g.d, off));
+    CU(cudaMemcpyAsync(g.d, g.h, f.coef_count * sizeof(int16_t), cudaMemcpyHostToDevice, 0));
+    uint16_t quant[3][64];
+    std::memset(quant, 0, sizeof(quant));
+    JpegColourArgs A;
+    std::memset(&A, 0, sizeof(A));
+    JpegPlane* planes[3] = {&A.Y, &A.Cb, &A.Cr};
+    for (int k = 0; k < f.ncomp; ++k) {
+        const rt_host::JpegComponent& C = f.comp[k];
+        std::memcpy(quant[k], f.quant[C.tq], sizeof(quant[k]));
+        JpegPlane& P = *planes[k];
+        P.coef = reinterpret_cast<const int16_t*>(g.d) + C.coef_offset;
+        P.samples = g.d + plane_off[k];
+        P.blocks_w = C.blocks_w; P.blocks_h = C.blocks_h; P.pitch = C.blocks_w * 8;
+        P.ds_w = C.ds_w; P.ds_h = C.ds_h; P.h = C.h; P.v = C.v;
+    }
+    CU(cudaMemcpyToSymbolAsync(c_jpeg_quant, quant, sizeof(quant), 0, cudaMemcpyHostToDevice, 0));
+    for (int k = 0; k < f.ncomp; ++k) {
+        const int n_blocks = planes[k]->blocks_w * planes[k]->blocks_h;
+        jpeg_idct_kernel<<<(n_blocks + 127) / 128, 128>>>(*planes[k], k);
+    }
+    A.mode = mode; A.rgb_passthrough = f.adobe_rgb ? 1 : 0; A.width = f.width; A.height = f.height;
+    jpeg_colour_kernel<<<dim3((unsigned)((f.width + 1023) / 1024), (unsigned)f.height), 256>>>(A, g.d + rgb_off);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(host_rgb8, g.d + rgb_off, need, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+// The same contract as rt_jpeg_decode through the nvJPEG library (not byte-identical to libjpeg: see rt_b200.h).
+int rt_jpeg_decode_nvjpeg(rt_context* c, const uint8_t* jpeg, size_t n_bytes, int* width, int* height, uint8_t* host_rgb8, size_t capacity) {
+    if (!c || !jpeg || !width || !height || n_bytes == 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_jpeg_decode_nvjpeg: null argument");
+    int rc = load_nvjpeg();
+    if (rc < 0) return rc;
+    CU(cudaSetDevice(c->device));
+    nvjpegHandle_t h = nullptr;
+    nvjpegJpegState_t st = nullptr;
+    if (g_nvjpeg.CreateSimple(&h) != NVJPEG_STATUS_SUCCESS) return fail(RT_ERR_CUDA, "nvjpegCreateSimple failed");
+    struct Guard { nvjpegHandle_t h; nvjpegJpegState_t* st; unsigned char* d = nullptr;
+                   ~Guard() { if (d) cudaFree(d); if (*st) g_nvjpeg.JpegStateDestroy(*st); g_nvjpeg.Destroy(h); } } guard{h, &st};
+    int comps = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t sub;
+    if (g_nvjpeg.GetImageInfo(h, jpeg, n_bytes, &comps, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS)
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_jpeg_decode_nvjpeg: not a JPEG stream nvJPEG can read");
+    *width = ws[0];
+    *height = hs[0];
+    if (!host_rgb8) return RT_OK;
+    const size_t need = (size_t)ws[0] * (size_t)hs[0] * 3;
+    if (capacity < need) return fail(RT_ERR_OUT_OF_RANGE, "rt_jpeg_decode_nvjpeg: capacity too small");
+    if (g_nvjpeg.JpegStateCreate(h, &st) != NVJPEG_STATUS_SUCCESS) return fail(RT_ERR_CUDA, "nvjpegJpegStateCreate failed");
+    CU(cudaMalloc(&guard.d, need));
+    nvjpegImage_t img;
+    std::memset(&img, 0, sizeof(img));
+    img.channel[0] = guard.d;
+    img.pitch[0] = (size_t)ws[0] * 3;
+    if (g_nvjpeg.Decode(h, st, jpeg, n_bytes, NVJPEG_OUTPUT_RGBI, &img, 0) != NVJPEG_STATUS_SUCCESS)
+        return fail(RT_ERR_CUDA, "nvjpegDecode failed");
+    CU(cudaMemcpy(host_rgb8, guard.d, need, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
 
 int rt_context_create(int device_id, rt_context** out) {
     if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_context_create: out is null");

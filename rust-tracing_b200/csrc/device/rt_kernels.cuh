@@ -593,21 +593,22 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ops& ops, 
 
 // ------------------------------------------------------------------ textures
 struct PerlinShared {
-    const float4* vec;      // shared memory
+    const float4* vec;      // shared memory: the first n_shared tables of the scene
     const uint8_t* perm;    // shared memory
+    int n_shared;           // tables beyond this many are read from global memory (every NoiseTexture::new owns a table,
+                            // texture.rs:100; four fit beside the render kernel's other shared data)
 };
 
-__device__ __forceinline__ float perlin_noise(const PerlinShared& P, int table, float3 p) {   // perlin.rs:27-50,81-100
+// perlin.rs:27-50,81-100. rv: 256 gradients, perm: perm_x | perm_y | perm_z of this table (shared or global memory).
+__device__ __forceinline__ float perlin_noise(const float4* rv, const uint8_t* px, float3 p) {
     const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     const int i = (int)fx, j = (int)fy, k = (int)fz;
     const float u = p.x - fx, v = p.y - fy, w = p.z - fz;
     const float uu = u * u * (3.0f - 2.0f * u);
     const float vv = v * v * (3.0f - 2.0f * v);
     const float ww = w * w * (3.0f - 2.0f * w);
-    const uint8_t* px = P.perm + table * 768;
     const uint8_t* py = px + 256;
     const uint8_t* pz = px + 512;
-    const float4* rv = P.vec + table * 256;
     const int xi[2] = {px[i & 255], px[(i + 1) & 255]};
     const int yi[2] = {py[j & 255], py[(j + 1) & 255]};
     const int zi[2] = {pz[k & 255], pz[(k + 1) & 255]};
@@ -625,15 +626,31 @@ __device__ __forceinline__ float perlin_noise(const PerlinShared& P, int table, 
     return acc;
 }
 
-__device__ __noinline__ float perlin_turbulence(const PerlinShared& P, int table, float3 p) {   // perlin.rs:52-64, depth 7
+// perlin.rs:52-64, depth 7. Two out-of-line copies, one per address space of the tables; a scene with up to four
+// NoiseTextures only ever runs the shared-memory one.
+__device__ __noinline__ float perlin_turbulence_shared(const float4* rv, const uint8_t* perm, float3 p) {
     float acc = 0.0f, w = 1.0f;
 #pragma unroll 1
     for (int o = 0; o < 7; ++o) {
-        acc = fmaf(w, perlin_noise(P, table, p), acc);
+        acc = fmaf(w, perlin_noise(rv, perm, p), acc);
         w *= 0.5f;
         p = p * 2.0f;
     }
     return fabsf(acc);
+}
+__device__ __noinline__ float perlin_turbulence_global(const float4* __restrict__ rv, const uint8_t* __restrict__ perm, float3 p) {
+    float acc = 0.0f, w = 1.0f;
+#pragma unroll 1
+    for (int o = 0; o < 7; ++o) {
+        acc = fmaf(w, perlin_noise(rv, perm, p), acc);
+        w *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(acc);
+}
+__device__ __forceinline__ float perlin_turbulence(const DevScene& S, const PerlinShared& P, int table, float3 p) {
+    if (table < P.n_shared) return perlin_turbulence_shared(P.vec + table * 256, P.perm + table * 768, p);
+    return perlin_turbulence_global(S.perlin_vec + table * 256, S.perlin_perm + table * 768, p);
 }
 
 // Texture::value (texture.rs:12-14). One out-of-line copy: it is called once per shaded hit, and keeping it (and
@@ -658,7 +675,7 @@ __device__ __noinline__ float3 texture_value(const DevScene& S, const PerlinShar
             const uint32_t j = (uint32_t)(vc * (float)(im.height - 1));
             return f3(__ldg(im.texels + (size_t)j * im.width + i));
         } else {                                // texture.rs:107-111
-            const float s = sinf(t0.w * p.z + 10.0f * perlin_turbulence(P, fbits(t0.y), p)) * 0.5f + 0.5f;
+            const float s = sinf(t0.w * p.z + 10.0f * perlin_turbulence(S, P, fbits(t0.y), p)) * 0.5f + 0.5f;
             return f3(s, s, s);
         }
     }

@@ -536,6 +536,38 @@ int rt_hit_bvh_nodes(rt_builder* b, const rt_bvh_node_desc* nodes, int n) {
     return (int)b->hittables.size() - 1;
 }
 
+// BVHNode::new_from_objects with the sorting done on the GPU (bvh_build.cuh): same seeded axis stream, same topology
+// rule, same node array as rt_hit_bvh - bit for bit (tests/test_gpu_bvh_build.py).
+extern "C" int rt_bvh_axis_draws(int n);
+extern "C" int rt_bvh_build_device(rt_context* c, const double* bboxes, int n, const int32_t* axes, rt_bvh_node_desc* nodes_out,
+                                   int32_t* order_out);
+int rt_hit_bvh_device(rt_builder* b, rt_context* ctx, const int* ids, int n) {
+    if (!b || !ids || !ctx) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_bvh_device: null argument");
+    if (n <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_hit_bvh_device: a BVH needs at least one object");
+    std::vector<double> boxes((size_t)n * 6);
+    for (int i = 0; i < n; ++i) {
+        if (!valid_id(ids[i], b->hittables.size())) return fail(RT_ERR_OUT_OF_RANGE, "rt_hit_bvh_device: unknown hittable id");
+        std::memcpy(&boxes[(size_t)i * 6], b->hittables[ids[i]].bbox, 48);
+    }
+    std::vector<int32_t> axes((size_t)rt_bvh_axis_draws(n));
+    for (int32_t& a : axes) a = b->axis_rng.range_inclusive(0, 2);   // the draws rt_hit_bvh makes, in its order (pre-order)
+    std::vector<rt_bvh_node_desc> nodes((size_t)(2 * n - 1));
+    const int made = rt_bvh_build_device(ctx, boxes.data(), n, axes.data(), nodes.data(), nullptr);
+    if (made < 0) return made;
+    const int32_t first = (int32_t)b->bvh_nodes.size();
+    for (rt_bvh_node_desc nd : nodes) {
+        if (nd.object >= 0) nd.object = ids[nd.object];   // position in `ids` -> hittable id
+        else { nd.left += first; nd.right += first; }
+        b->bvh_nodes.push_back(nd);
+    }
+    rt_hittable_desc h = blank_hittable(RT_HIT_BVH);
+    h.child = first;
+    h.count = 2 * n - 1;
+    std::memcpy(h.bbox, nodes[0].bbox, sizeof(h.bbox));
+    b->hittables.push_back(h);
+    return (int)b->hittables.size() - 1;
+}
+
 int rt_builder_finish(rt_builder* b, int world, rt_scene_desc* out) {
     if (!b || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_builder_finish: null argument");
     if (!valid_id(world, b->hittables.size())) return fail(RT_ERR_OUT_OF_RANGE, "rt_builder_finish: unknown world id");

@@ -150,6 +150,33 @@ def test_textures_against_golden(rt, ctx):
     ds.close()
 
 
+def test_more_noise_textures_than_fit_in_shared_memory(rt, ob, ctx):
+    """Every NoiseTexture::new owns a Perlin table (texture.rs:100). Four are staged in shared memory; the rest are read
+    from global memory - same values either way, checked per texture against the oracle and through a render."""
+    s = rt.Scene()
+    noises = [s.NoiseTexture(1.0 + k, perlin_seed=10 + k) for k in range(7)]
+    l = rt.HittableList()
+    for k, t in enumerate(noises):
+        l.add(s.Sphere((3.0 * (k - 3), 0, -8), 1.3, s.Lambertian(t)))
+    s.finish(s.BVHNode(l))
+    ds = ctx.upload(s)
+    rng = np.random.default_rng(5)
+    uvp = np.concatenate([rng.uniform(0, 1, (2000, 2)), rng.uniform(-20, 20, (2000, 3))], axis=1)
+    vals = []
+    for t in noises:
+        dev = ctx.texture_batch(ds, t, uvp)
+        ref = ob.texture_batch(s.desc, int(t), uvp)
+        assert np.abs(dev - ref).max() <= 2e-3 and np.abs(dev - ref).mean() <= 1e-4
+        vals.append(dev[:, 0])
+    assert all(np.abs(vals[0] - v).mean() > 0.05 for v in vals[1:])          # seven different tables, not one
+    cam = rt.Camera(rt.CameraSettings(image_width=160, aspect_ratio=2.5, samples_per_pixel=4, max_depth=6, vfov=70.0,
+                                      background=(0.7, 0.8, 1.0)))
+    dev = ctx.render(ds, cam, 0, 4, seed=1)
+    ref, _ = ob.render(s.desc, cam, 0, 4, seed=1, mode=0)
+    assert agreement(dev, ref, 4, tol=5e-3) >= 0.98
+    ds.close()
+
+
 @pytest.mark.parametrize("name", ["random_balls", "final_scene"])
 def test_camera_rays_against_golden(rt, ctx, name):
     g = np.load(os.path.join(GOLD, f"camera_{name}.npz"))
