@@ -24,6 +24,7 @@ DEPS = SOURCES + [
     os.path.join(CSRC, "device", "dev_scene.h"),
     os.path.join(CSRC, "device", "rt_kernels.cuh"),
     os.path.join(CSRC, "device", "render_mk.cuh"),
+    os.path.join(CSRC, "device", "render_q.cuh"),
     os.path.join(CSRC, "device", "bvh_build.cuh"),
     os.path.join(CSRC, "device", "jpeg_kernels.cuh"),
     os.path.join(CSRC, "host", "jpeg_entropy.h"),

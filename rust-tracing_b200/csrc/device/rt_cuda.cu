@@ -50,6 +50,12 @@ struct RenderParams {
     int shade_min;               // the shade class may win the vote once this many lanes wait for it
     int slab_fast;               // lanes in the slab class that skip the full vote
     int sphere_reps, quad_reps;  // consecutive sphere / quad ops per vote
+    // render_q.cuh (paths decoupled from lanes)
+    unsigned long long* path_counter;   // next global path number
+    unsigned long long total_paths;     // sample_count x tiles x 32
+    int xchg_min;                // finished segments in a warp that trigger an exchange
+    int slab_drop;               // a box-test round ends once this many lanes have left the class
+    int min_trav;                // a traversal warp with fewer slots than this looks at the SHADE queue
 };
 
 // op counters of the instrumented kernel (rt_render_count_ops): what the device traversal actually executes
@@ -75,6 +81,9 @@ __device__ __forceinline__ void set_ops_base(OpsGlobal& o, const float4* g) { o.
 __device__ __forceinline__ void set_ops_base(OpsShared&, const float4*) {}
 
 #include "render_mk.cuh"
+#ifdef RT_B200_DEV
+#include "render_q.cuh"   // measured alternative (paths decoupled from lanes through shared-memory queues): A/B build only
+#endif
 
 struct DevRayIn { float ox, oy, oz, dx, dy, dz, time, pad; };
 struct DevHitOut { float t, px, py, pz, nx, ny, nz, u, v; int hit, front_face, prim, mat; };
@@ -231,6 +240,10 @@ static render_fn mk_kernel(bool counting, bool ops_smem) {
     return ops_smem ? render_kernel_mk<false, true> : render_kernel_mk<false, false>;
 }
 
+#ifdef RT_B200_DEV
+static render_fn q_kernel(bool ops_smem) { return ops_smem ? render_kernel_q<true> : render_kernel_q<false>; }
+#endif
+
 // rt_render_accumulate may be called on several streams of one context: every launch takes its own work counter and
 // statistics block from a ring, zeroed on the launching stream, so launches in flight never share them.
 constexpr int kLaunchSlots = 64;
@@ -247,6 +260,9 @@ struct rt_context {
     int shade_min = 24, slab_fast = 6, sphere_reps = 2, quad_reps = 8;   // measured plateaus: profiles/r2_sweep*.log
     bool hoist_media = true, prune_boxes = true, box_primitives = true, ops_in_smem = true;
     int chunk = 8;
+    bool queue_kernel = false;                 // A/B build only: render_q.cuh instead of render_mk.cuh (RT_B200_KERNEL=q)
+    int xchg_min = 8, slab_drop = 8, min_trav = 24;
+    unsigned long long* d_path_counters = nullptr;   // kLaunchSlots path counters (render_q.cuh)
     unsigned int* d_counters = nullptr;        // kLaunchSlots work counters
     unsigned long long* d_stats = nullptr;     // kLaunchSlots x K_NUM
     int last_slot = 0;
@@ -275,6 +291,7 @@ struct rt_scene {
 static void context_free(rt_context* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_counters);
+    cudaFree(c->d_path_counters);
     cudaFree(c->d_stats);
     cudaFree(c->d_fb);
     cudaFree(c->d_rgb8);
@@ -500,11 +517,20 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* v = std::getenv("RT_B200_NO_HOIST")) c->hoist_media = std::atoi(v) == 0;
     if (const char* v = std::getenv("RT_B200_OPS_GLOBAL")) c->ops_in_smem = std::atoi(v) == 0;
     if (const char* v = std::getenv("RT_B200_CHUNK")) c->chunk = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("RT_B200_KERNEL")) c->queue_kernel = std::string(v) == "q";
+    if (const char* v = std::getenv("RT_B200_XCHG_MIN")) c->xchg_min = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("RT_B200_SLAB_DROP")) c->slab_drop = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("RT_B200_MIN_TRAV")) c->min_trav = std::max(1, std::atoi(v));
 #endif
     for (int counting = 0; counting < 2; ++counting)
         for (int in_smem = 0; in_smem < 2; ++in_smem)
             CU(cudaFuncSetAttribute(mk_kernel(counting != 0, in_smem != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+#ifdef RT_B200_DEV
+    for (int in_smem = 0; in_smem < 2; ++in_smem)
+        CU(cudaFuncSetAttribute(q_kernel(in_smem != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+#endif
     CU(cudaMalloc(&c->d_counters, kLaunchSlots * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_path_counters, kLaunchSlots * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->d_stats, (size_t)kLaunchSlots * K_NUM * sizeof(unsigned long long)));
     CU(cudaMemset(c->d_stats, 0, (size_t)kLaunchSlots * K_NUM * sizeof(unsigned long long)));
     for (int k = 0; k < 2; ++k) {
@@ -724,16 +750,39 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     prm.slab_fast = c->slab_fast;
     prm.sphere_reps = c->sphere_reps;
     prm.quad_reps = c->quad_reps;
-    // the op stream rides in shared memory when it fits beside the per-thread path state and the Perlin tables
-    MkSmem lay = mk_smem_layout(s->ops_bytes, s->dev.n_perlin);
-    const bool in_smem = c->ops_in_smem && !s->ops_in_global && lay.total <= c->smem_optin;
-    if (!in_smem) lay = mk_smem_layout(0, s->dev.n_perlin);
-    if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: per-thread state does not fit in shared memory");
-    prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
-    CU(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned int), stream));
+    prm.path_counter = nullptr;
+    prm.total_paths = 0;
+    prm.xchg_min = prm.slab_drop = prm.min_trav = 0;
     CU(cudaMemsetAsync(prm.stats, 0, K_NUM * sizeof(unsigned long long), stream));
-    render_fn fn = mk_kernel(counting, in_smem);
-    fn<<<c->sm_count, kRenderThreads, lay.total, stream>>>(prm);
+#ifdef RT_B200_DEV
+    if (c->queue_kernel && !counting) {
+        // render_q.cuh: paths numbered globally, 32 per (tile, sample)
+        if ((uint64_t)n_tiles * (uint64_t)sample_count >= 0xffffffffull) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_accumulate: too many work items; split the sample range");
+        prm.path_counter = c->d_path_counters + slot;
+        prm.total_paths = (unsigned long long)n_tiles * (unsigned long long)sample_count * 32ull;
+        prm.xchg_min = c->xchg_min;
+        prm.slab_drop = c->slab_drop;
+        prm.min_trav = c->min_trav;
+        QSmem lay = q_smem_layout(s->ops_bytes, s->dev.n_perlin);
+        const bool in_smem = c->ops_in_smem && !s->ops_in_global && lay.total <= c->smem_optin;
+        if (!in_smem) lay = q_smem_layout(0, s->dev.n_perlin);
+        if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: path slots do not fit in shared memory");
+        prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
+        CU(cudaMemsetAsync(prm.path_counter, 0, sizeof(unsigned long long), stream));
+        q_kernel(in_smem)<<<c->sm_count, kQThreads, lay.total, stream>>>(prm);
+    } else
+#endif
+    {
+        // the op stream rides in shared memory when it fits beside the per-thread path state and the Perlin tables
+        MkSmem lay = mk_smem_layout(s->ops_bytes, s->dev.n_perlin);
+        const bool in_smem = c->ops_in_smem && !s->ops_in_global && lay.total <= c->smem_optin;
+        if (!in_smem) lay = mk_smem_layout(0, s->dev.n_perlin);
+        if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: per-thread state does not fit in shared memory");
+        prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
+        CU(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned int), stream));
+        render_fn fn = mk_kernel(counting, in_smem);
+        fn<<<c->sm_count, kRenderThreads, lay.total, stream>>>(prm);
+    }
     CU(cudaGetLastError());
     c->last_slot = slot;
     c->launches += 1;

@@ -11,7 +11,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["RT_B200_LIB"] = os.path.join(ROOT, "rust-tracing_b200", "csrc", "librt_b200_dev.so")
+os.environ.setdefault("RT_B200_LIB", os.path.join(ROOT, "rust-tracing_b200", "csrc", "librt_b200_dev.so"))
 
 
 def main():
