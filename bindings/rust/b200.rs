@@ -173,6 +173,9 @@ extern "C" {
     pub fn rt_hit_rotate_y_sincos(b: *mut rt_builder, object: c_int, sin_theta: c_double, cos_theta: c_double) -> c_int;
     pub fn rt_hit_constant_medium_nid(b: *mut rt_builder, boundary: c_int, neg_inv_density: c_double, albedo_tex: c_int) -> c_int;
     pub fn rt_hit_bvh_nodes(b: *mut rt_builder, nodes: *const rt_bvh_node_desc, n: c_int) -> c_int;
+    pub fn rt_hit_bvh_device(b: *mut rt_builder, ctx: *mut rt_context, ids: *const c_int, n: c_int) -> c_int;
+    pub fn rt_jpeg_decode(ctx: *mut rt_context, jpeg: *const u8, n_bytes: usize, width: *mut c_int, height: *mut c_int,
+                          host_rgb8: *mut u8, capacity: usize) -> c_int;
     pub fn rt_builder_finish(b: *mut rt_builder, world: c_int, out: *mut rt_scene_desc) -> c_int;
     pub fn rt_context_create(device_id: c_int, out: *mut *mut rt_context) -> c_int;
     pub fn rt_context_destroy(ctx: *mut rt_context);
