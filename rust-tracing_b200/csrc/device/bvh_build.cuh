@@ -75,19 +75,28 @@ __global__ void bvh_pair_kernel(const double* __restrict__ bbox, int* __restrict
     if (!(bbox[(size_t)a * 6 + 2 * ax] < bbox[(size_t)b * 6 + 2 * ax])) { perm[calls[c].start] = b; perm[calls[c].start + 1] = a; }
 }
 
-// one thread per call: the box of its range
+// one WARP per call: the box of its range (lanes stride over the range, fmin / fmax butterflies; exact and order-independent)
 __global__ void bvh_box_kernel(const double* __restrict__ bbox, const int* __restrict__ perm, const BvhCall* __restrict__ calls,
                                int n_calls, double* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= n_calls) return;
-    double b[6];
-    const double* f = bbox + (size_t)perm[calls[c].start] * 6;
-    for (int k = 0; k < 6; ++k) b[k] = f[k];
-    for (int j = 1; j < calls[c].span; ++j) {
-        const double* g = bbox + (size_t)perm[calls[c].start + j] * 6;
+    const int start = calls[c].start, span = calls[c].span;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double b[6] = {inf, -inf, inf, -inf, inf, -inf};
+    for (int j = lane; j < span; j += 32) {
+        const double* g = bbox + (size_t)perm[start + j] * 6;
         for (int k = 0; k < 3; ++k) { b[2 * k] = fmin(b[2 * k], g[2 * k]); b[2 * k + 1] = fmax(b[2 * k + 1], g[2 * k + 1]); }
     }
-    for (int k = 0; k < 6; ++k) out[(size_t)c * 6 + k] = b[k];
+    for (int off = 16; off > 0; off >>= 1)
+        for (int k = 0; k < 3; ++k) {
+            b[2 * k] = fmin(b[2 * k], __shfl_xor_sync(0xffffffffu, b[2 * k], off));
+            b[2 * k + 1] = fmax(b[2 * k + 1], __shfl_xor_sync(0xffffffffu, b[2 * k + 1], off));
+        }
+    double v = b[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) if (lane == k) v = b[k];
+    if (lane < 6) out[(size_t)c * 6 + lane] = v;
 }
 
 void bvh_shape(int start, int span, int level, const int32_t* axes, int* next_axis, int* next_node, std::vector<BvhCall>* calls) {
@@ -152,7 +161,7 @@ extern "C" int rt_bvh_build_device(rt_context* c, const double* bboxes, int n, c
     }
     const unsigned cblocks = (unsigned)((calls.size() + 127) / 128);
     bvh_pair_kernel<<<cblocks, 128>>>(d_bbox, d_perm[cur], d_calls, (int)calls.size());
-    bvh_box_kernel<<<cblocks, 128>>>(d_bbox, d_perm[cur], d_calls, (int)calls.size(), d_boxes);
+    bvh_box_kernel<<<(unsigned)((calls.size() * 32 + 127) / 128), 128>>>(d_bbox, d_perm[cur], d_calls, (int)calls.size(), d_boxes);
     CU(cudaGetLastError());
     std::vector<int> order((size_t)n);
     std::vector<double> boxes(calls.size() * 6);

@@ -84,8 +84,12 @@ __device__ __forceinline__ void idct8(const int in[8], int out[8], int shift) {
     out[4] = jdescale(tmp13 - t0, shift);
 }
 
-__global__ void __launch_bounds__(128) jpeg_idct_kernel(JpegPlane P, int comp) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+struct JpegIdctArgs { JpegPlane plane[3]; int first_cta[4]; };   // CTAs [first_cta[c], first_cta[c + 1]) work on component c
+
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(JpegIdctArgs A) {
+    const int comp = (int)blockIdx.x >= A.first_cta[2] ? 2 : ((int)blockIdx.x >= A.first_cta[1] ? 1 : 0);
+    const JpegPlane& P = A.plane[comp];
+    const int b = ((int)blockIdx.x - A.first_cta[comp]) * blockDim.x + threadIdx.x;
     if (b >= P.blocks_w * P.blocks_h) return;
     const uint4* src = reinterpret_cast<const uint4*>(P.coef + (size_t)b * 64);
     int ws[8][8];
@@ -194,7 +198,96 @@ __device__ __forceinline__ uint32_t jpeg_pixel(const JpegColourArgs& A, int x, i
     return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 
-// one thread per four pixels of a row: 12 output bytes = three aligned 32-bit stores when the width is a multiple of 4
+__device__ __forceinline__ uint32_t jpeg_ycc_rgb(int yy, int cb, int cr) {   // jdcolor.c ycc_rgb_convert, packed r | g << 8 | b << 16
+    const int u = cb - 128, w = cr - 128;
+    const int r = min(255, max(0, yy + ((91881 * w + 32768) >> 16)));
+    const int g = min(255, max(0, yy + ((-22554 * u + 32768 - 46802 * w) >> 16)));
+    const int b = min(255, max(0, yy + ((116130 * u + 32768) >> 16)));
+    return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+}
+
+// Four chroma samples [c0, c0 + 4) of a row as one 32-bit load plus the two neighbours the triangle filter needs, the
+// neighbour index clamped at the row's ends: with prev = this (next = this) the filter's general form gives exactly
+// jdsample.c's special first / last column ((4 this + 8) >> 4, (4 this + 7) >> 4; h2v1: this).
+__device__ __forceinline__ void chroma_window(const uint8_t* row, int c0, int ds_w, int v[6]) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(row + c0);     // pitch and c0 are multiples of 4
+    v[1] = (int)(w & 0xffu); v[2] = (int)((w >> 8) & 0xffu); v[3] = (int)((w >> 16) & 0xffu); v[4] = (int)(w >> 24);
+    v[0] = c0 > 0 ? (int)row[c0 - 1] : v[1];
+    v[5] = c0 + 4 < ds_w ? (int)row[c0 + 4] : v[4];
+    // a row whose real samples end inside this window: the last real sample is its own neighbour
+    if (c0 + 3 >= ds_w) {
+#pragma unroll
+        for (int k = 2; k <= 4; ++k) if (c0 + k - 1 >= ds_w) v[k] = v[k - 1];
+    }
+}
+
+// Fast form for widths that are a multiple of 8 (the reference's 6400 x 3200 asset): one thread per eight pixels of a row -
+// 8 luma bytes as one 64-bit load, the chroma of both planes through chroma_window, 24 output bytes as three 64-bit
+// stores. Byte for byte the arithmetic of jpeg_pixel.
+__global__ void __launch_bounds__(256) jpeg_colour8_kernel(JpegColourArgs A, uint8_t* __restrict__ rgb) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8, y = blockIdx.y;
+    if (x0 >= A.width) return;
+    const uint2 yw = *reinterpret_cast<const uint2*>(A.Y.samples + (size_t)y * A.Y.pitch + x0);
+    int yy[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { yy[k] = (int)((yw.x >> (8 * k)) & 0xffu); yy[4 + k] = (int)((yw.y >> (8 * k)) & 0xffu); }
+    int cb[8], cr[8];
+    if (A.mode == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { cb[k] = 128; cr[k] = 128; }
+    } else if (A.mode == 1) {
+        const uint2 bw = *reinterpret_cast<const uint2*>(A.Cb.samples + (size_t)y * A.Cb.pitch + x0);
+        const uint2 rw = *reinterpret_cast<const uint2*>(A.Cr.samples + (size_t)y * A.Cr.pitch + x0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cb[k] = (int)((bw.x >> (8 * k)) & 0xffu); cb[4 + k] = (int)((bw.y >> (8 * k)) & 0xffu);
+            cr[k] = (int)((rw.x >> (8 * k)) & 0xffu); cr[4 + k] = (int)((rw.y >> (8 * k)) & 0xffu);
+        }
+    } else {
+        const int c0 = x0 >> 1;
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+            const JpegPlane& C = plane ? A.Cr : A.Cb;
+            int* out = plane ? cr : cb;
+            int s[6];
+            if (A.mode == 2) {          // h2v1: the samples themselves, 2 fraction bits
+                chroma_window(C.samples + (size_t)y * C.pitch, c0, C.ds_w, s);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    out[2 * k] = (3 * s[k + 1] + s[k] + 1) >> 2;
+                    out[2 * k + 1] = (3 * s[k + 1] + s[k + 2] + 2) >> 2;
+                }
+            } else {                    // h2v2: column sums 3 * nearer row + further row, 4 fraction bits
+                const int cy = y >> 1;
+                const int fy = (y & 1) ? min(cy + 1, C.ds_h - 1) : max(cy - 1, 0);
+                int f[6];
+                chroma_window(C.samples + (size_t)cy * C.pitch, c0, C.ds_w, s);
+                chroma_window(C.samples + (size_t)fy * C.pitch, c0, C.ds_w, f);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s[k] = 3 * s[k] + f[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    out[2 * k] = (3 * s[k + 1] + s[k] + 8) >> 4;
+                    out[2 * k + 1] = (3 * s[k + 1] + s[k + 2] + 7) >> 4;
+                }
+            }
+        }
+    }
+    uint32_t px[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (A.mode == 0) px[k] = (uint32_t)yy[k] * 0x010101u;
+        else if (A.rgb_passthrough) px[k] = (uint32_t)yy[k] | ((uint32_t)cb[k] << 8) | ((uint32_t)cr[k] << 16);
+        else px[k] = jpeg_ycc_rgb(yy[k], cb[k], cr[k]);
+    }
+    uint2* o = reinterpret_cast<uint2*>(rgb + ((size_t)y * A.width + x0) * 3);     // 24-byte groups: 8-byte aligned
+    o[0] = make_uint2(px[0] | (px[1] << 24), (px[1] >> 8) | (px[2] << 16));
+    o[1] = make_uint2((px[2] >> 16) | (px[3] << 8), px[4] | (px[5] << 24));
+    o[2] = make_uint2((px[5] >> 8) | (px[6] << 16), (px[6] >> 16) | (px[7] << 8));
+}
+
+// General form (any width): one thread per four pixels of a row; 12 output bytes = three aligned 32-bit stores when the
+// width is a multiple of 4.
 __global__ void __launch_bounds__(256) jpeg_colour_kernel(JpegColourArgs A, uint8_t* __restrict__ rgb) {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x0 >= A.width) return;

@@ -270,6 +270,10 @@ struct rt_context {
     size_t fb_pixels = 0;
     uint8_t* d_rgb8 = nullptr;                 // rt_finalize_rgb8's output
     size_t rgb8_bytes = 0;
+    void* h_jpeg = nullptr;                    // rt_jpeg_decode: pinned coefficients and the device block, kept between calls
+    size_t h_jpeg_bytes = 0;
+    unsigned char* d_jpeg = nullptr;
+    size_t d_jpeg_bytes = 0;
     void* h_stage[2] = {nullptr, nullptr};     // pinned staging
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
     std::vector<std::pair<void*, size_t>> free_blocks;   // device blocks released by rt_scene_destroy, reused by the next upload
@@ -292,6 +296,8 @@ static void context_free(rt_context* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_counters);
     cudaFree(c->d_path_counters);
+    cudaFree(c->d_jpeg);
+    if (c->h_jpeg) cudaFreeHost(c->h_jpeg);
     cudaFree(c->d_stats);
     cudaFree(c->d_fb);
     cudaFree(c->d_rgb8);
@@ -412,9 +418,16 @@ int rt_jpeg_decode(rt_context* c, const uint8_t* jpeg, size_t n_bytes, int* widt
     }
     CU(cudaSetDevice(c->device));
     // pinned coefficients (the Huffman decoder writes them where the DMA engine reads them), one device block for
-    // coefficients + sample planes + RGB
-    struct Guard { int16_t* h = nullptr; unsigned char* d = nullptr; ~Guard() { if (h) cudaFreeHost(h); if (d) cudaFree(d); } } g;
-    CU(cudaMallocHost(&g.h, f.coef_count * sizeof(int16_t)));
+    // coefficients + sample planes + RGB; both are kept in the context and grown on demand
+    struct { int16_t* h; unsigned char* d; } g{nullptr, nullptr};
+    const size_t coef_bytes = f.coef_count * sizeof(int16_t);
+    if (c->h_jpeg_bytes < coef_bytes) {
+        if (c->h_jpeg) cudaFreeHost(c->h_jpeg);
+        c->h_jpeg = nullptr; c->h_jpeg_bytes = 0;
+        CU(cudaMallocHost(&c->h_jpeg, coef_bytes));
+        c->h_jpeg_bytes = coef_bytes;
+    }
+    g.h = static_cast<int16_t*>(c->h_jpeg);
     rc = rt_host::jpeg_entropy_decode(jpeg, n_bytes, &f, g.h, f.coef_count, &err);
     if (rc < 0) return fail(rc, "rt_jpeg_decode: " + err);
     size_t plane_off[3], off = (f.coef_count * sizeof(int16_t) + 255) & ~(size_t)255;
@@ -424,8 +437,14 @@ int rt_jpeg_decode(rt_context* c, const uint8_t* jpeg, size_t n_bytes, int* widt
     }
     const size_t rgb_off = off;
     off += need;
-    CU(cudaMalloc(&g.d, off));
-    CU(cudaMemcpyAsync(g.d, g.h, f.coef_count * sizeof(int16_t), cudaMemcpyHostToDevice, 0));
+    if (c->d_jpeg_bytes < off) {
+        cudaFree(c->d_jpeg);
+        c->d_jpeg = nullptr; c->d_jpeg_bytes = 0;
+        CU(cudaMalloc(&c->d_jpeg, off));
+        c->d_jpeg_bytes = off;
+    }
+    g.d = c->d_jpeg;
+    CU(cudaMemcpyAsync(g.d, g.h, coef_bytes, cudaMemcpyHostToDevice, 0));
     uint16_t quant[3][64];
     std::memset(quant, 0, sizeof(quant));
     JpegColourArgs A;
@@ -441,12 +460,21 @@ int rt_jpeg_decode(rt_context* c, const uint8_t* jpeg, size_t n_bytes, int* widt
         P.ds_w = C.ds_w; P.ds_h = C.ds_h; P.h = C.h; P.v = C.v;
     }
     CU(cudaMemcpyToSymbolAsync(c_jpeg_quant, quant, sizeof(quant), 0, cudaMemcpyHostToDevice, 0));
-    for (int k = 0; k < f.ncomp; ++k) {
-        const int n_blocks = planes[k]->blocks_w * planes[k]->blocks_h;
-        jpeg_idct_kernel<<<(n_blocks + 127) / 128, 128>>>(*planes[k], k);
+    JpegIdctArgs I;
+    std::memset(&I, 0, sizeof(I));
+    int ctas = 0;
+    for (int k = 0; k < 3; ++k) {
+        I.first_cta[k] = ctas;
+        if (k < f.ncomp) { I.plane[k] = *planes[k]; ctas += (planes[k]->blocks_w * planes[k]->blocks_h + 127) / 128; }
     }
+    I.first_cta[3] = ctas;
+    jpeg_idct_kernel<<<ctas, 128>>>(I);
     A.mode = mode; A.rgb_passthrough = f.adobe_rgb ? 1 : 0; A.width = f.width; A.height = f.height;
-    jpeg_colour_kernel<<<dim3((unsigned)((f.width + 1023) / 1024), (unsigned)f.height), 256>>>(A, g.d + rgb_off);
+    // chroma_window reads whole 32-bit words of a chroma row: fine for every plane (pitch = blocks x 8), and the fast form
+    // needs rows of whole 8-pixel groups and more than two chroma samples (jdsample.c: fancy upsampling only then)
+    const bool fast = (f.width % 8) == 0 && (f.ncomp == 1 || A.Cb.ds_w > 2);
+    if (fast) jpeg_colour8_kernel<<<dim3((unsigned)((f.width / 8 + 255) / 256), (unsigned)f.height), 256>>>(A, g.d + rgb_off);
+    else jpeg_colour_kernel<<<dim3((unsigned)((f.width + 1023) / 1024), (unsigned)f.height), 256>>>(A, g.d + rgb_off);
     CU(cudaGetLastError());
     CU(cudaMemcpy(host_rgb8, g.d + rgb_off, need, cudaMemcpyDeviceToHost));
     return RT_OK;

@@ -54,6 +54,22 @@ struct BitReader {
     bool hit_marker = false;
 
     void fill() {
+        // fast path: the next eight bytes hold no 0xff (no stuffing, no marker) - take as many whole bytes as fit
+        if (!hit_marker && p + 8 <= end) {
+            uint64_t v;
+            std::memcpy(&v, p, 8);
+            if (!(((v ^ 0xffffffffffffffffull) - 0x0101010101010101ull) & ~(v ^ 0xffffffffffffffffull) & 0x8080808080808080ull)) {
+                v = __builtin_bswap64(v);
+                const int nb = (64 - n) >> 3;
+                if (nb > 0) {
+                    const uint64_t chunk = nb == 8 ? v : (v >> (64 - 8 * nb));
+                    acc |= nb == 8 ? chunk : (chunk << (64 - n - 8 * nb));
+                    n += 8 * nb;
+                    p += nb;
+                }
+                return;
+            }
+        }
         while (n <= 56) {
             int byte = 0;
             if (!hit_marker && p < end) {

@@ -44,6 +44,7 @@ def test_struct_sizes_match_header(rt):
     assert C.sizeof(A.PerlinDesc) == 256 * 24 + 3 * 1024
     assert C.sizeof(A.RayDesc) == 56 and A.ray_dtype().itemsize == 56
     assert C.sizeof(A.HitDesc) == 88 and A.hit_dtype().itemsize == 88
+    assert C.sizeof(A.JpegInfo) == 16 * 4 + 3 * 64 * 2 + 4 * 8          # rt_jpeg_info
 
 
 def test_error_codes_and_messages(rt):
