@@ -29,12 +29,12 @@ def main(argv=None):
     from PIL import Image
     import rust_tracing_b200 as rt
     scene = args.scene if 0 <= args.scene <= 8 else 0       # main.rs:655
-    earth = rt.load_earth(args.earth)[0] if scene in (2, 8) else None
+    ctx = rt.Context(args.device)
+    earth = rt.load_earth(args.earth, ctx=ctx)[0] if scene in (2, 8) else None   # ImageTexture::new's decode, on the device
     t0 = time.time()
     s, cs = rt.builtin_scene(scene, image_width=args.width, samples_per_pixel=args.spp, max_depth=args.depth, earth=earth)
     cam = rt.Camera(cs)
     print(f"Building BVH: {time.time() - t0:.2f}s")          # main.rs:660 (scene + BVH build on the host)
-    ctx = rt.Context(args.device)
     ds = ctx.upload(s)
     t0 = time.time()
     if args.live:

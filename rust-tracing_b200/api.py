@@ -240,9 +240,9 @@ def jpeg_entropy_decode(data):
     return info, coef
 
 
-def load_earth(path=None):
-    """The decoded earth image (texture.rs:76-80 decodes `assets/earth-large.jpg`, main.rs:179,591), PIL-decoded to
-    RGB8. Looked for, in order: `path`, $RT_B200_EARTH, ./assets/earth-large.jpg, <repo>/assets/earth-large.jpg (the
+def load_earth(path=None, ctx=None):
+    """The decoded earth image (texture.rs:76-80 decodes `assets/earth-large.jpg`, main.rs:179,591) as RGB8: decoded on
+    the GPU by rt_jpeg_decode when a Context is given (same bytes), by PIL otherwise. Looked for, in order: `path`, $RT_B200_EARTH, ./assets/earth-large.jpg, <repo>/assets/earth-large.jpg (the
     byte copy tools/make_reference_fixtures.py / build() make where the reference checkout exists; it travels to the
     GPU box) and the reference checkout itself. Only if none exists: the synthetic stand-in, and the source string
     says so. Returns (array, source)."""
@@ -251,6 +251,9 @@ def load_earth(path=None):
                   os.path.join(os.environ.get("RT_REFERENCE", "/root/reference"), "assets", "earth-large.jpg")]
     for p in candidates:
         if p and os.path.exists(p):
+            if ctx is not None and p.lower().endswith((".jpg", ".jpeg")):
+                with open(p, "rb") as f:
+                    return ctx.jpeg_decode(f.read()), p
             from PIL import Image
             Image.MAX_IMAGE_PIXELS = None
             return np.asarray(Image.open(p).convert("RGB"), dtype=np.uint8), p

@@ -41,6 +41,7 @@ def test_own_decoder_on_the_reference_earth_image(rt, ctx):
     earth, src = rt.load_earth()
     if "synthetic" not in src:
         assert np.array_equal(dev, earth)
+        assert np.array_equal(rt.load_earth(ctx=ctx)[0], earth)     # the CLI's path: decoded on the device
 
 
 def test_image_texture_from_device_decoded_jpeg(rt, ob, ctx):
