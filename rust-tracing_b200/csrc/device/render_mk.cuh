@@ -222,7 +222,7 @@ __device__ __noinline__ uint32_t shade_phase(uint32_t link, unsigned* cnt) {
     if (start) {   // world.hit(ray, [0.001, inf)) begins: hoisted media first, then the op stream from word 0
         const float3 so = f3(COLD(F_WO), COLD(F_WO + 1), COLD(F_WO + 2));
         const float3 sd = f3(COLD(F_WD), COLD(F_WD + 1), COLD(F_WD + 2));
-        const float a = dot(sd, sd), inv_a = 1.0f / a;
+        const float a = dot(sd, sd), inv_a = frcp(a);
         COLD(F_O) = so.x; COLD(F_O + 1) = so.y; COLD(F_O + 2) = so.z;
         COLD(F_D) = sd.x; COLD(F_D + 1) = sd.y; COLD(F_D + 2) = sd.z;
         COLD(F_A) = a; COLD(F_INVA) = inv_a;

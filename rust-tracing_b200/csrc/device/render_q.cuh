@@ -201,7 +201,7 @@ __device__ __noinline__ unsigned q_shade_batch(unsigned rot) {   // returns (seg
     if (start) {   // world.hit(ray, [0.001, inf)) begins: hoisted media first, then the op stream from word 0
         const float3 so = f3(ST(F_WO), ST(F_WO + 1), ST(F_WO + 2));
         const float3 sd = f3(ST(F_WD), ST(F_WD + 1), ST(F_WD + 2));
-        const float a = dot(sd, sd), inv_a = 1.0f / a;
+        const float a = dot(sd, sd), inv_a = frcp(a);
         ST(F_O) = so.x; ST(F_O + 1) = so.y; ST(F_O + 2) = so.z;
         ST(F_D) = sd.x; ST(F_D + 1) = sd.y; ST(F_D + 2) = sd.z;
         ST(F_A) = a; ST(F_INVA) = inv_a;

@@ -62,12 +62,32 @@ __device__ __forceinline__ float3 operator*(float s, float3 a) { return a * s; }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ float3 fma3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
 __device__ __forceinline__ float3 normalize3(float3 a) { return a * rsqrtf(dot(a, a)); }
+
+// Division, reciprocal and square root as ONE special-function instruction (+ one multiply for the division): the
+// `.approx.ftz` forms, 1-2 ulp like the `-prec-div=false -prec-sqrt=false` sequences the compiler emits for `/` and sqrtf,
+// but without their range fix-ups (operands beyond 2^126 or below 2^-126: 7-9 instructions per site). Geometry of this
+// path never gets there - a denormal direction component counts as zero, i.e. a ray parallel to that slab - and with ~35
+// executed division sites the fix-ups alone were 12% of the render kernel's active instruction footprint, which sits at the
+// edge of the 32 KB instruction cache (profiles/r2_k1_icache.md).
+#ifndef RT_OPT_NO_FASTDIV
+__device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fdiv(float a, float b) { float r; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+__device__ __forceinline__ float frcp(float x) { return 1.0f / x; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
+#endif
 __device__ __forceinline__ int fbits(float f) { return __float_as_int(f); }
 
 // ------------------------------------------------------------------ keyed RNG (shared spec with the oracle)
 // pcg4d (Jarzynski & Olano, JCGT 9(3) 2020). path key = pcg4d(pixel, sample, seed_lo, seed_hi);
 // draw(purpose) = pcg4d(key.x, key.y, key.z + segment, key.w + purpose); u01 = (x >> 8) * 2^-24.
+#ifdef RT_OPT_PCG_NOINLINE
+__device__ __noinline__ uint4 pcg4d(uint4 v) {
+#else
 __device__ __forceinline__ uint4 pcg4d(uint4 v) {
+#endif
     v.x = v.x * 1664525u + 1013904223u; v.y = v.y * 1664525u + 1013904223u;
     v.z = v.z * 1664525u + 1013904223u; v.w = v.w * 1664525u + 1013904223u;
     v.x += v.y * v.w; v.y += v.z * v.x; v.z += v.x * v.y; v.w += v.y * v.z;
@@ -87,7 +107,7 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0
 // loop-free samplers with the distributions of vec3.rs:54-65 (rejection loops in the reference)
 __device__ __forceinline__ float3 unit_vector(float u0, float u1) {
     const float z = 1.0f - 2.0f * u0;
-    const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    const float r = fsqrt(fmaxf(0.0f, 1.0f - z * z));
     float s, c;
     sincospif(2.0f * u1, &s, &c);
     return f3(r * c, r * s, z);
@@ -130,7 +150,7 @@ struct RaySetup {
     float eps;              // 2^-21 max_k |o_k / d_k| over the axes with a finite quotient
     float a, inv_a;         // |d|^2 and its reciprocal (sphere tests)
 };
-__device__ __forceinline__ float3 safe_inv(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+__device__ __forceinline__ float3 safe_inv(float3 d) { return f3(frcp(d.x), frcp(d.y), frcp(d.z)); }
 __device__ __forceinline__ RaySetup ray_setup(float3 o, float3 d) {
     RaySetup R;
     R.inv = safe_inv(d);
@@ -139,7 +159,7 @@ __device__ __forceinline__ RaySetup ray_setup(float3 o, float3 d) {
     const float ex = fabsf(R.oi.x), ey = fabsf(R.oi.y), ez = fabsf(R.oi.z);   // NaN (0 * inf) and inf axes constrain nothing
     R.eps = 4.76837158e-7f * fmaxf(fmaxf(ex < inf ? ex : 0.0f, ey < inf ? ey : 0.0f), ez < inf ? ez : 0.0f);
     R.a = dot(d, d);
-    R.inv_a = 1.0f / R.a;
+    R.inv_a = frcp(R.a);
     return R;
 }
 
@@ -221,18 +241,18 @@ __device__ __forceinline__ bool sphere_roots_f32(float3 oc, float3 d, float a, f
     const float3 l = fma3(-hb * inv_a, d, oc);
     const float disc = fmaf(r, r, -dot(l, l));
     if (disc < 0.0f) return false;
-    const float sq = sqrtf(disc * a);
+    const float sq = fsqrt(disc * a);
     const float cc = fmaf(-r, r, dot(oc, oc));
     const float nan = __int_as_float(0x7fc00000);
     float near_root, far_root;
     if (hb > 0.0f) {            // both roots via q to avoid -hb + sq cancellation
         const float q = -hb - sq;
         near_root = q * inv_a;
-        far_root = self_origin ? nan : cc / q;
+        far_root = self_origin ? nan : fdiv(cc, q);
     } else {
         const float q = -hb + sq;
         far_root = q * inv_a;
-        near_root = self_origin ? nan : cc / q;
+        near_root = self_origin ? nan : fdiv(cc, q);
     }
     *r1 = near_root;
     *r2 = far_root;
@@ -292,7 +312,7 @@ __device__ __forceinline__ bool quad_test(const Ops& ops, uint32_t link, float4 
     const uint32_t at = link & kLinkMask;
     const float4 w3 = ops(at + 48u);
     if (fabsf(denom) < 1e-8f || starts_on(origin, link)) return false;   // quad.rs:110-112; a ray cannot re-hit the plane it starts on
-    const float t = (w3.x - dot(n, o)) / denom;
+    const float t = fdiv(w3.x - dot(n, o), denom);
     if (!(tmin <= t && t <= tmax)) return false;                          // ray_t.contains: closed (quad.rs:115)
     const float4 w2 = ops(at + 32u);
     const float3 p = fma3(t, d, o);
@@ -382,11 +402,11 @@ __device__ __forceinline__ bool medium_test(const DevScene& S, const Ops& ops, u
     t2 = fminf(t2, tmax);
     if (!(t1 < t2)) return false;
     t1 = fmaxf(t1, 0.0f);
-    const float ray_length = sqrtf(a);
+    const float ray_length = fsqrt(a);
     const float inside = (t2 - t1) * ray_length;
     const float u = u01(draw(key, seg, P_MEDIUM + (uint32_t)fbits(w0.z)).x);
     const float hit_distance = w0.x * logf(u);   // drawn only on this branch (constant_medium.rs:48)
-    *t_out = t1 + hit_distance / ray_length;
+    *t_out = t1 + fdiv(hit_distance, ray_length);
     return hit_distance <= inside;
 }
 
@@ -489,8 +509,8 @@ __device__ __forceinline__ void sphere_uv(float3 n, float* u, float* v) {   // s
     const float PI = 3.14159265358979323846f;
     const float theta = acosf(-n.y);
     const float phi = atan2f(-n.z, n.x) + PI;
-    *u = phi / (2.0f * PI);
-    *v = theta / PI;
+    *u = phi * (0.5f / PI);
+    *v = theta * (1.0f / PI);
 }
 
 // hit point in f64 relative to the centre: keeps the normal of a huge sphere accurate
@@ -530,7 +550,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ops& ops, 
         } else {
             float3 c = f3(w0);
             if (flags & FLAG_MOVING) c = fma3(ray.time, f3(ops(at + 32u)), c);
-            outward = (pl - c) * (1.0f / w1.x);   // (p - center) / radius, reciprocal-multiply (vec3.rs:244-249)
+            outward = (pl - c) * frcp(w1.x);   // (p - center) / radius, reciprocal-multiply (vec3.rs:244-249)
         }
         h.mat = fbits(w1.y);
         h.prim = fbits(w1.z);
@@ -563,7 +583,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ops& ops, 
         { const float m = fabsf(ty0 - t); if (m <= miss) { miss = m; face = 5; tf = ty0; } }
         t = tf;
         const float3 pl = fma3(t, d, o);
-        const float ex = 1.0f / (hi.x - lo.x), ey = 1.0f / (hi.y - lo.y), ez = 1.0f / (hi.z - lo.z);
+        const float ex = frcp(hi.x - lo.x), ey = frcp(hi.y - lo.y), ez = frcp(hi.z - lo.z);
         const float ax = (pl.x - lo.x) * ex, ay = (pl.y - lo.y) * ey, az = (pl.z - lo.z) * ez;   // 0..1 along +x,+y,+z
         outward = f3(0.0f, 0.0f, 0.0f);
         switch (face) {   // (u, v) = (alpha, beta) of the face's quad (quad.rs:55-90)
@@ -694,11 +714,11 @@ __device__ __forceinline__ bool shade(const DevScene& S, const PerlinShared& P, 
     float3 dir = h.normal, att = f3(1.0f, 1.0f, 1.0f);
     bool scattered = true;
     if (kind == RT_MAT_DIELECTRIC) {          // material.rs:81-103
-        const float ratio = h.front_face ? 1.0f / m0.z : m0.z;
+        const float ratio = h.front_face ? frcp(m0.z) : m0.z;
         const float3 unit = normalize3(ray.d);
         const float cos_theta = fminf(dot(-unit, h.normal), 1.0f);
-        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-        float r0 = (1.0f - ratio) / (1.0f + ratio);
+        const float sin_theta = fsqrt(1.0f - cos_theta * cos_theta);
+        float r0 = fdiv(1.0f - ratio, 1.0f + ratio);
         r0 = r0 * r0;
         const float x = 1.0f - cos_theta;
         const float refl = r0 + (1.0f - r0) * (x * x * x * x * x);           // material.rs:74-78
@@ -706,7 +726,7 @@ __device__ __forceinline__ bool shade(const DevScene& S, const PerlinShared& P, 
             dir = reflect3(unit, h.normal);
         } else {                                                               // vec3.rs:96-101
             const float3 perp = ratio * (unit + cos_theta * h.normal);
-            dir = perp + (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * h.normal;
+            dir = perp + (-fsqrt(fabsf(1.0f - dot(perp, perp)))) * h.normal;
         }
     } else if (kind != RT_MAT_DIFFUSE_LIGHT) {
         const uint4 r = draw(key, seg, P_SCATTER);
