@@ -61,7 +61,6 @@ __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x *
 __device__ __forceinline__ float3 operator*(float s, float3 a) { return a * s; }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ float3 fma3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
-__device__ __forceinline__ float3 normalize3(float3 a) { return a * rsqrtf(dot(a, a)); }
 
 // Division, reciprocal and square root as ONE special-function instruction (+ one multiply for the division): the
 // `.approx.ftz` forms, 1-2 ulp like the `-prec-div=false -prec-sqrt=false` sequences the compiler emits for `/` and sqrtf,
@@ -73,12 +72,27 @@ __device__ __forceinline__ float3 normalize3(float3 a) { return a * rsqrtf(dot(a
 __device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fdiv(float a, float b) { float r; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float frsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// sin and cos of 2 pi u, u in [0, 1): the special-function unit on the argument folded to [-pi, pi) (absolute error
+// 2^-20.9 there), sign restored: sin(2 pi u) = -sin(2 pi u - pi)
+__device__ __forceinline__ void fsincos_turn(float u, float* s, float* c) {
+    const float a = fmaf(u, 6.283185307179586f, -3.141592653589793f);
+    float sn, cs;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(a));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(a));
+    *s = -sn;
+    *c = -cs;
+}
 #else
+__device__ __forceinline__ float frsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ void fsincos_turn(float u, float* s, float* c) { sincospif(2.0f * u, s, c); }
 __device__ __forceinline__ float frcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 __device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
 #endif
 __device__ __forceinline__ int fbits(float f) { return __float_as_int(f); }
+
+__device__ __forceinline__ float3 normalize3(float3 a) { return a * frsqrt(dot(a, a)); }
 
 // ------------------------------------------------------------------ keyed RNG (shared spec with the oracle)
 // pcg4d (Jarzynski & Olano, JCGT 9(3) 2020). path key = pcg4d(pixel, sample, seed_lo, seed_hi);
@@ -109,7 +123,7 @@ __device__ __forceinline__ float3 unit_vector(float u0, float u1) {
     const float z = 1.0f - 2.0f * u0;
     const float r = fsqrt(fmaxf(0.0f, 1.0f - z * z));
     float s, c;
-    sincospif(2.0f * u1, &s, &c);
+    fsincos_turn(u1, &s, &c);
     return f3(r * c, r * s, z);
 }
 
@@ -629,7 +643,7 @@ __device__ __forceinline__ float perlin_noise(const float4* rv, const uint8_t* p
     const float ww = w * w * (3.0f - 2.0f * w);
     const uint8_t* py = px + 256;
     const uint8_t* pz = px + 512;
-    const int xi[2] = {px[i & 255], px[(i + 1) & 255]};
+    const int xi0 = px[i & 255], xi1 = px[(i + 1) & 255];
     const int yi[2] = {py[j & 255], py[(j + 1) & 255]};
     const int zi[2] = {pz[k & 255], pz[(k + 1) & 255]};
     float acc = 0.0f;
@@ -639,7 +653,7 @@ __device__ __forceinline__ float perlin_noise(const float4* rv, const uint8_t* p
         for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const float4 g = rv[xi[a] ^ yi[b] ^ zi[c]];
+                const float4 g = rv[(a ? xi1 : xi0) ^ yi[b] ^ zi[c]];
                 const float wa = a ? uu : 1.0f - uu, wb = b ? vv : 1.0f - vv, wc = c ? ww : 1.0f - ww;
                 acc += wa * wb * wc * (g.x * (u - (float)a) + g.y * (v - (float)b) + g.z * (w - (float)c));
             }
@@ -773,7 +787,7 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera& C, int px, int py, ui
         const uint4 e = draw(key, 0u, P_CAMERA_DISK);
         const float rad = sqrtf(u01(e.x));
         float s, c;
-        sincospif(2.0f * u01(e.y), &s, &c);
+        fsincos_turn(u01(e.y), &s, &c);
         const float3 off = (rad * c) * C.disk_u + (rad * s) * C.disk_v;      // camera.rs:128-131
         ray.o = C.center + off;
         rel = rel - off;
