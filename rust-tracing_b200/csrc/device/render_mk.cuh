@@ -20,7 +20,11 @@
 //  * the repetition loop ends with one ballot + popc + compare (no repetition counter);
 //  * shading, path regeneration and segment start are ONE out-of-line function (shade_phase): its register needs no
 //    longer decide what the traversal loop may keep in registers (the inlined form spilled the loop's own per-ray
-//    constants and reloaded them in every repetition). Everything the two sides share lives in shared memory.
+//    constants and reloaded them in every repetition). Everything the two sides share lives in shared memory;
+//  * the code this kernel EXECUTES on final_scene (2 100 of its 6 000 instructions) sat at the edge of the 32 KB instruction
+//    cache: divisions, reciprocals and square roots are single special-function instructions now (rt_kernels.cuh frcp /
+//    fdiv / fsqrt) instead of the compiler's range-fix-up sequences - 9% fewer instructions, +23% Mpaths/s
+//    (profiles/r2_k1_icache.md). Keep that in mind before inlining anything else into the shade phase.
 //
 // Included by rt_cuda.cu.
 #pragma once
