@@ -41,7 +41,7 @@ enum OpKind : uint32_t {
                          //   local = R(x - a) + b, R = rotate-y (hittable.rs:164-168), x = the WORLD ray: the transform is the
                          //   composition with every enclosing instance; the box (padded, centre / half extent) is in the
                          //   enclosing space; skip = the op after the matching exit
-    OP_XFORM_EXIT = 4,   // w0 = {parent OP_XFORM_ENTER (word index, -1 = world space), 0, 0, hdr}   w1 = {0,0,0,0}   size 2
+    OP_XFORM_EXIT = 4,   // w0 = {parent OP_XFORM_ENTER (word index, -1 = world space), 0, 0, hdr}   w1 = {0,0,0,0}   size 2, FLAG_ALWAYS
     OP_MEDIUM = 5,       // body of a ConstantMedium; always preceded by an OP_INNER holding its box (skip = past the medium)
                          // w0 = {neg_inv_density, mat, prim_id, hdr(flags = boundary kind)}
                          //   boundary sphere : w1 = {c.xyz, r}  w2 = {center_vec.xyz, precise_idx | aux<<24}             size 3
@@ -49,8 +49,9 @@ enum OpKind : uint32_t {
                          //                     the fall-through successor is the op at bend                              size 3
                          //   boundary xbox   : w1 = {a.xyz, sin} w2 = {b.xyz, cos} w3 = {min.xyz, 0} w4 = {max.xyz, 0}   size 5
     OP_BOX = 6,          // a Quad::cube list as ONE slab primitive:                                                      size 4
-                         //   w0 = {c.xyz, hdr} w1 = {h.xyz, mat} (centre / half extent of the exact corners, NOT padded)
-                         //   w2 = {min.xyz, first_quad_prim_id} w3 = {max.xyz, 0} (the exact corners: hit record, self-origin rule)
+                         //   w0 = {c.xyz, hdr} w1 = {h.xyz, fall-through link} (centre / half extent of the exact corners, NOT padded;
+                         //   the link makes "the ray misses this box" the same arithmetic as a rejected OP_INNER)
+                         //   w2 = {min.xyz, first_quad_prim_id} w3 = {max.xyz, mat} (the exact corners: hit record, self-origin rule)
                          //   faces in quad.rs:45-93 order: 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y ; prim_id = first + face
     OP_INNER_REF = 7,    // w0 = {lo.xyz, hdr} w1 = {hi.xyz, skip link}: the reference's own node box and aabb.rs:64-84 verbatim
                          //   (per axis, never narrowed). Emitted for every BVH node - leaves included, bvh.rs:92 tests them too -
@@ -61,6 +62,7 @@ enum OpKind : uint32_t {
 
 constexpr uint32_t FLAG_MOVING = 1u;   // sphere has center_vec
 constexpr uint32_t FLAG_PRECISE = 2u;  // sphere test runs in f64 (huge radius; SURVEY.md §7 "hard parts")
+constexpr uint32_t FLAG_ALWAYS = 8u;   // box-headed op whose own code runs whatever the box arithmetic says (OP_XFORM_EXIT, OP_INNER_REF)
 
 constexpr int MEDIUM_BOUNDARY_SPHERE = 0;
 constexpr int MEDIUM_BOUNDARY_PROGRAM = 1;
@@ -73,6 +75,7 @@ enum OpClass : uint32_t { CLS_SLAB = 0, CLS_SPHERE = 1, CLS_QUAD = 2, CLS_MEDIUM
 constexpr uint32_t kLinkMask = 0x0fffffffu;        // byte offset part of a link
 constexpr uint32_t kHdrFallThrough = 0xf00000ffu;  // size in bytes | successor class << 28
 constexpr uint32_t kHdrNotInner = 0x0fffff00u;     // zero for OP_INNER: then link + hdr is the fall-through link
+constexpr uint32_t kHdrAlwaysRare = FLAG_ALWAYS << 12;
 constexpr uint32_t kSlabLimit = 1u << 28;          // link < kSlabLimit  <=>  the lane is in the slab class
 inline uint32_t make_hdr(uint32_t kind, uint32_t flags, uint32_t size_words) { return (size_words * 16u) | (kind << 8) | (flags << 12); }
 inline uint32_t hdr_kind(uint32_t hdr) { return (hdr >> 8) & 15u; }

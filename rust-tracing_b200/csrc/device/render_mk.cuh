@@ -266,7 +266,7 @@ __device__ __noinline__ uint32_t medium_phase(uint32_t link) {
     return ((uint32_t)next_word << 4) | ((uint32_t)fbits(w0.w) & 0xf0000000u);
 }
 
-template <bool COUNT, bool OPS_SMEM>
+template <bool COUNT, bool OPS_SMEM, bool FOLD>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const RenderParams prm_in) {
     unsigned char* smem = reinterpret_cast<unsigned char*>(dyn_smem);
     const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
@@ -335,12 +335,14 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
         COLD(F_A) = R__.a; COLD(F_INVA) = R__.inv_a;                                               \
     } while (0)
 
+    // The loop's top is the full vote. The box-test loop is entered either as the vote's pick (a minority round: it lasts
+    // until half of its lanes have left the class) or straight after another class has run, when at least slab_fast lanes
+    // stand at box-headed ops (no second vote, no dispatch). It leaves with its last lane count, which the next vote uses.
+    unsigned n_slab = 0u;
     for (;;) {
-        // ---- the vote
-        unsigned n_slab = __popc(__ballot_sync(0xffffffffu, link < kSlabLimit));
-        unsigned pick = CLS_SLAB, stay = (unsigned)slab_fast;
-        if (n_slab < (unsigned)slab_fast) {
-            // lanes per class: five 6-bit counters in one REDUX (CLS_NEED counts as CLS_SHADE, CLS_IDLE as nothing)
+        // ---- the vote: lanes per class, five 6-bit counters in one REDUX (CLS_NEED counts as CLS_SHADE, CLS_IDLE as nothing)
+        unsigned pick = CLS_SLAB;
+        {
             unsigned cls = link >> 28;
             if (cls == CLS_NEED) cls = CLS_SHADE;
             const unsigned tot = __reduce_add_sync(0xffffffffu, cls < CLS_IDLE ? (1u << (6 * cls)) : 0u);
@@ -355,133 +357,147 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                 if (c_med > best_n) { pick = CLS_MEDIUM; best_n = c_med; }
                 if (best_n == 0u) pick = CLS_SHADE;
             }
-            stay = max(1u, (n_slab + 1u) >> 1);      // a minority slab round lasts until half of its lanes have left the class
             if (COUNT && (tid & 31) == 0) cnt[K_VOTES]++;
         }
         if (COUNT) cnt[K_LANE_OPS] += ((link >> 28) == pick);
-
-        if (pick == CLS_SLAB) {
-            // ---- cull boxes, cube primitives, instance enter / exit: the box-test loop
+        unsigned stay = max(1u, (n_slab + 1u) >> 1);
+        if (pick != CLS_SLAB) {
+            if (pick == CLS_SPHERE) {
 #pragma unroll 1
-            do {
-                if (link < kSlabLimit) {
-                    float te, tx;
-                    slab_ch(w0, w1, inv, oi, &te, &tx);
-                    const uint32_t hdr = (uint32_t)fbits(w0.w);
-                    if ((hdr & kHdrNotInner) == 0u) {          // OP_INNER: AABB::hit (aabb.rs:64-84)
-                        CNT(K_SLAB);
-                        link = cull_pass(te, tx, tmin, best_t, eps) ? link + hdr : (uint32_t)fbits(w1.w);
-                    } else {
-                        const uint32_t kind = (hdr >> 8) & 15u;
-                        const uint32_t ft = link + (hdr & kHdrFallThrough);
-                        if (kind == OP_BOX) {                  // Quad::cube as one slab primitive (box_accept)
-                            CNT(K_BOX);
-                            float t;
-                            bool win;
-                            const int origin = COLD_I(F_ORIGIN);
-                            if (!starts_on(origin, link)) {
-                                win = box_accept(te, tx, tmin, best_t, &t);
-                            } else {
-                                // The ray starts on a face of this very box. Leaving it (the direction points out of that face,
-                                // as every ray scattered off an opaque box does) it cannot hit the box again; going in
-                                // (refraction) it takes the exact form, which knows the plane it stands on.
-                                const int face = origin & 7;   // 0 +z, 1 +x, 2 -z, 3 -x, 4 +y, 5 -y
-                                const float ia = (face == 1 || face == 3) ? inv.x : (face >= 4 ? inv.y : inv.z);
-                                const bool max_side = face == 0 || face == 1 || face == 4;
-                                win = (ia > 0.0f) != max_side &&
-                                      box_test_from_face(ops(link + 32u), ops(link + 48u), CUR_O(), inv, tmin, best_t, face, &t);
-                            }
-                            if (win) { best_t = t; best_op = (int)(link >> 4); best_xf = COLD_I(F_XF); CNT(K_BOX_HIT); }
-                            link = ft;
-                        } else if (kind == OP_XFORM_ENTER) {   // Translate::hit / RotateY::hit (hittable.rs:96-111,159-193)
-                            CNT(K_SLAB);
-                            if (!cull_pass(te, tx, tmin, best_t, eps)) {
-                                link = (uint32_t)fbits(w1.w);
-                            } else {
-                                CNT(K_XFORM_ENTER);
-                                const float4 w2 = ops(link + 32u), w3 = ops(link + 48u);
-                                const float3 lo_ = xform_point(f3(COLD(F_WO), COLD(F_WO + 1), COLD(F_WO + 2)), w2, w3);
-                                const float3 ld_ = xform_dir(f3(COLD(F_WD), COLD(F_WD + 1), COLD(F_WD + 2)), w2, w3);
-                                SET_RAY(lo_, ld_);             // the op holds the composed world -> local transform
-                                COLD_I(F_XF) = (int)(link >> 4);
-                                link = ft;
-                            }
-                        } else if (kind == OP_XFORM_EXIT) {    // back in the enclosing space
-                            const int parent = fbits(w0.x);
-                            float3 lo_ = f3(COLD(F_WO), COLD(F_WO + 1), COLD(F_WO + 2));
-                            float3 ld_ = f3(COLD(F_WD), COLD(F_WD + 1), COLD(F_WD + 2));
-                            if (parent >= 0) {
-                                const float4 p2 = ops(((uint32_t)parent << 4) + 32u), p3 = ops(((uint32_t)parent << 4) + 48u);
-                                lo_ = xform_point(lo_, p2, p3);
-                                ld_ = xform_dir(ld_, p2, p3);
-                            }
-                            SET_RAY(lo_, ld_);
-                            COLD_I(F_XF) = parent;
-                            link = ft;
-                        } else {                               // OP_INNER_REF: the reference's box, the reference's test
-                            CNT(K_SLAB);
-                            link = aabb_hit_reference(w0, w1, CUR_O(), inv, tmin, best_t) ? ft : (uint32_t)fbits(w1.w);
+                for (int rep = 0; rep < sphere_reps; ++rep) {
+                    if ((link >> 28) == CLS_SPHERE) {
+                        const uint32_t hdr = (uint32_t)fbits(w0.w);
+                        CNT(K_SPHERE);
+                        if (COUNT) { if ((hdr >> 12) & FLAG_MOVING) cnt[K_SPHERE_MOVING]++; if ((hdr >> 12) & FLAG_PRECISE) cnt[K_SPHERE_PRECISE]++; }
+                        float t;
+                        if (sphere_test(S, ops, link, w0, w1, CUR_O(), CUR_D(), COLD(F_A), COLD(F_INVA), COLD(F_TIME), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
+                            best_t = t; best_op = (int)((link & kLinkMask) >> 4); best_xf = COLD_I(F_XF);
+                            CNT(K_SPHERE_HIT);
                         }
+                        link = (link & kLinkMask) + (hdr & kHdrFallThrough);
+                        FETCH_NEXT();
                     }
-                    FETCH_NEXT();
+                    if (!__any_sync(0xffffffffu, (link >> 28) == CLS_SPHERE)) break;
                 }
-                n_slab = __popc(__ballot_sync(0xffffffffu, link < kSlabLimit));
-            } while (n_slab >= stay);
-        } else if (pick == CLS_SPHERE) {
+            } else if (pick == CLS_QUAD) {
 #pragma unroll 1
-            for (int rep = 0; rep < sphere_reps; ++rep) {
-                if ((link >> 28) == CLS_SPHERE) {
-                    const uint32_t hdr = (uint32_t)fbits(w0.w);
-                    CNT(K_SPHERE);
-                    if (COUNT) { if ((hdr >> 12) & FLAG_MOVING) cnt[K_SPHERE_MOVING]++; if ((hdr >> 12) & FLAG_PRECISE) cnt[K_SPHERE_PRECISE]++; }
-                    float t;
-                    if (sphere_test(S, ops, link, w0, w1, CUR_O(), CUR_D(), COLD(F_A), COLD(F_INVA), COLD(F_TIME), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
-                        best_t = t; best_op = (int)((link & kLinkMask) >> 4); best_xf = COLD_I(F_XF);
-                        CNT(K_SPHERE_HIT);
+                for (int rep = 0; rep < quad_reps; ++rep) {      // lists of quads sit next to each other in the stream
+                    if ((link >> 28) == CLS_QUAD) {
+                        const uint32_t hdr = (uint32_t)fbits(w0.w);
+                        CNT(K_QUAD);
+                        float t;
+                        if (quad_test(ops, link, w0, w1, CUR_O(), CUR_D(), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
+                            best_t = t; best_op = (int)((link & kLinkMask) >> 4); best_xf = COLD_I(F_XF);
+                            CNT(K_QUAD_HIT);
+                        }
+                        link = (link & kLinkMask) + (hdr & kHdrFallThrough);
+                        FETCH_NEXT();
                     }
-                    link = (link & kLinkMask) + (hdr & kHdrFallThrough);
-                    FETCH_NEXT();
+                    if (!__any_sync(0xffffffffu, (link >> 28) == CLS_QUAD)) break;
                 }
-                if (!__any_sync(0xffffffffu, (link >> 28) == CLS_SPHERE)) break;
-            }
-        } else if (pick == CLS_QUAD) {
-#pragma unroll 1
-            for (int rep = 0; rep < quad_reps; ++rep) {      // lists of quads sit next to each other in the stream
-                if ((link >> 28) == CLS_QUAD) {
-                    const uint32_t hdr = (uint32_t)fbits(w0.w);
-                    CNT(K_QUAD);
-                    float t;
-                    if (quad_test(ops, link, w0, w1, CUR_O(), CUR_D(), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
-                        best_t = t; best_op = (int)((link & kLinkMask) >> 4); best_xf = COLD_I(F_XF);
-                        CNT(K_QUAD_HIT);
-                    }
-                    link = (link & kLinkMask) + (hdr & kHdrFallThrough);
-                    FETCH_NEXT();
+            } else if (pick == CLS_MEDIUM) {
+                if ((link >> 28) == CLS_MEDIUM) {     // a medium that could not be hoisted (inside an instance / generic boundary)
+                    CNT(K_MEDIUM);
+                    COLD(F_BEST_T) = best_t; COLD_I(F_BEST_OP) = best_op; COLD_I(F_BEST_XF) = best_xf;
+                    link = medium_phase<Ops>(link);
                 }
-                if (!__any_sync(0xffffffffu, (link >> 28) == CLS_QUAD)) break;
-            }
-        } else if (pick == CLS_MEDIUM) {
-            if ((link >> 28) == CLS_MEDIUM) {     // a medium that could not be hoisted (inside an instance / generic boundary)
-                CNT(K_MEDIUM);
+                const RaySetup R = ray_setup(CUR_O(), CUR_D());      // nothing live across the call (see the shade branch)
+                inv = R.inv; oi = R.oi; eps = R.eps;
+                best_t = COLD(F_BEST_T); best_op = COLD_I(F_BEST_OP); best_xf = COLD_I(F_BEST_XF);
+                FETCH_NEXT();
+            } else {
+                // ---- shade / regenerate / start segments, out of line. Nothing of the traversal state stays in registers
+                // across the call: the closest hit is parked in shared memory, the per-ray constants are re-derived from the
+                // current ray, the op words are fetched again (once per ~25 box tests of every lane: cheap, and it frees the
+                // register allocation of the box-test loop from the needs of the shading code).
                 COLD(F_BEST_T) = best_t; COLD_I(F_BEST_OP) = best_op; COLD_I(F_BEST_XF) = best_xf;
-                link = medium_phase<Ops>(link);
+                link = shade_phase<COUNT, Ops>(link, cnt);
+                const RaySetup R = ray_setup(CUR_O(), CUR_D());
+                inv = R.inv; oi = R.oi; eps = R.eps;
+                best_t = COLD(F_BEST_T); best_op = COLD_I(F_BEST_OP); best_xf = COLD_I(F_BEST_XF);
+                FETCH_NEXT();
             }
-            const RaySetup R = ray_setup(CUR_O(), CUR_D());      // nothing live across the call (see the shade branch)
-            inv = R.inv; oi = R.oi; eps = R.eps;
-            best_t = COLD(F_BEST_T); best_op = COLD_I(F_BEST_OP); best_xf = COLD_I(F_BEST_XF);
-            FETCH_NEXT();
-        } else {
-            // ---- shade / regenerate / start segments, out of line. Nothing of the traversal state stays in registers
-            // across the call: the closest hit is parked in shared memory, the per-ray constants are re-derived from the
-            // current ray, the op words are fetched again (once per ~25 box tests of every lane: cheap, and it frees the
-            // register allocation of the box-test loop from the needs of the shading code).
-            COLD(F_BEST_T) = best_t; COLD_I(F_BEST_OP) = best_op; COLD_I(F_BEST_XF) = best_xf;
-            link = shade_phase<COUNT, Ops>(link, cnt);
-            const RaySetup R = ray_setup(CUR_O(), CUR_D());
-            inv = R.inv; oi = R.oi; eps = R.eps;
-            best_t = COLD(F_BEST_T); best_op = COLD_I(F_BEST_OP); best_xf = COLD_I(F_BEST_XF);
-            FETCH_NEXT();
+            n_slab = __popc(__ballot_sync(0xffffffffu, link < kSlabLimit));
+            if (n_slab < (unsigned)slab_fast) continue;
+            stay = (unsigned)slab_fast;
+            if (COUNT) cnt[K_LANE_OPS] += (link < kSlabLimit);
         }
+        // ---- cull boxes, cube primitives, instance enter / exit: the box-test loop
+#pragma unroll 1
+        do {
+            // every lane runs the box arithmetic on whatever op words it holds (lanes of other classes: harmless, their
+            // link and words are kept), so the common case has no divergent branch at all
+            const bool in_class = link < kSlabLimit;
+            float te, tx;
+            slab_ch(w0, w1, inv, oi, &te, &tx);
+            const uint32_t hdr = (uint32_t)fbits(w0.w);
+            const bool pass = cull_pass(te, tx, tmin, best_t, eps);
+            uint32_t nl = pass ? link + hdr : (uint32_t)fbits(w1.w);      // OP_INNER: AABB::hit (aabb.rs:64-84)
+            // FOLD (scenes with cube primitives or instances): a cube or an instance whose box the ray misses is finished
+            // by the arithmetic above - their second word ends with the link to follow then - and only the accepting
+            // side takes the rare branch. Three more instructions per repetition, so scenes without such ops go without.
+            const bool rare = in_class && (hdr & kHdrNotInner) != 0u && (!FOLD || pass || (hdr & kHdrAlwaysRare) != 0u);
+            if (COUNT && FOLD && in_class && (hdr & kHdrNotInner) != 0u && !rare) CNT(((hdr >> 8) & 15u) == OP_BOX ? K_BOX : K_SLAB);
+            if (rare) {
+                const uint32_t kind = (hdr >> 8) & 15u;
+                const uint32_t ft = link + (hdr & kHdrFallThrough);
+                nl = ft;
+                if (kind == OP_BOX) {
+                    CNT(K_BOX);
+                    float t;
+                    bool win;
+                    const int origin = COLD_I(F_ORIGIN);
+                    if (!starts_on(origin, link)) {
+                        win = box_accept(te, tx, tmin, best_t, &t);
+                    } else {
+                        const int face = origin & 7;
+                        const float ia = (face == 1 || face == 3) ? inv.x : (face >= 4 ? inv.y : inv.z);
+                        const bool max_side = face == 0 || face == 1 || face == 4;
+                        win = (ia > 0.0f) != max_side &&
+                              box_test_from_face(ops(link + 32u), ops(link + 48u), CUR_O(), inv, tmin, best_t, face, &t);
+                    }
+                    if (win) { best_t = t; best_op = (int)(link >> 4); best_xf = COLD_I(F_XF); CNT(K_BOX_HIT); }
+                } else if (kind == OP_XFORM_ENTER) {
+                    CNT(K_SLAB);
+                    if (!pass) {
+                        nl = (uint32_t)fbits(w1.w);
+                    } else {
+                        CNT(K_XFORM_ENTER);
+                        const float4 w2 = ops(link + 32u), w3 = ops(link + 48u);
+                        const float3 lo_ = xform_point(f3(COLD(F_WO), COLD(F_WO + 1), COLD(F_WO + 2)), w2, w3);
+                        const float3 ld_ = xform_dir(f3(COLD(F_WD), COLD(F_WD + 1), COLD(F_WD + 2)), w2, w3);
+                        SET_RAY(lo_, ld_);
+                        COLD_I(F_XF) = (int)(link >> 4);
+                    }
+                } else if (kind == OP_XFORM_EXIT) {
+                    const int parent = fbits(w0.x);
+                    float3 lo_ = f3(COLD(F_WO), COLD(F_WO + 1), COLD(F_WO + 2));
+                    float3 ld_ = f3(COLD(F_WD), COLD(F_WD + 1), COLD(F_WD + 2));
+                    if (parent >= 0) {
+                        const float4 p2 = ops(((uint32_t)parent << 4) + 32u), p3 = ops(((uint32_t)parent << 4) + 48u);
+                        lo_ = xform_point(lo_, p2, p3);
+                        ld_ = xform_dir(ld_, p2, p3);
+                    }
+                    SET_RAY(lo_, ld_);
+                    COLD_I(F_XF) = parent;
+                } else {
+                    CNT(K_SLAB);
+                    nl = aabb_hit_reference(w0, w1, CUR_O(), inv, tmin, best_t) ? ft : (uint32_t)fbits(w1.w);
+                }
+            } else if (COUNT && in_class) {
+                CNT(K_SLAB);
+            }
+            link = in_class ? nl : link;
+            if (OPS_SMEM) {   // predicated loads (the compiler would branch around them): lanes of other classes keep their words
+                asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %9, 0;\n@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%8];\n"
+                             "@p ld.shared.v4.f32 {%4, %5, %6, %7}, [%8+16];\n}"
+                             : "+f"(w0.x), "+f"(w0.y), "+f"(w0.z), "+f"(w0.w), "+f"(w1.x), "+f"(w1.y), "+f"(w1.z), "+f"(w1.w)
+                             : "r"(smem_addr + kSmemOps + (link & kLinkMask)), "r"((uint32_t)in_class));
+            } else if (in_class) {
+                FETCH_NEXT();
+            }
+            n_slab = __popc(__ballot_sync(0xffffffffu, link < kSlabLimit));
+        } while (n_slab >= stay);
     }
 #undef CNT
 #undef FETCH_NEXT

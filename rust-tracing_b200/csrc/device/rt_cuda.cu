@@ -235,9 +235,13 @@ DevCamera make_dev_camera(const rt_camera_desc& c) {
 }  // namespace
 
 typedef void (*render_fn)(const RenderParams);
-static render_fn mk_kernel(bool counting, bool ops_smem) {
-    if (counting) return ops_smem ? render_kernel_mk<true, true> : render_kernel_mk<true, false>;
-    return ops_smem ? render_kernel_mk<false, true> : render_kernel_mk<false, false>;
+static render_fn mk_kernel(bool counting, bool ops_smem, bool fold) {
+    if (fold) {
+        if (counting) return ops_smem ? render_kernel_mk<true, true, true> : render_kernel_mk<true, false, true>;
+        return ops_smem ? render_kernel_mk<false, true, true> : render_kernel_mk<false, false, true>;
+    }
+    if (counting) return ops_smem ? render_kernel_mk<true, true, false> : render_kernel_mk<true, false, false>;
+    return ops_smem ? render_kernel_mk<false, true, false> : render_kernel_mk<false, false, false>;
 }
 
 #ifdef RT_B200_DEV
@@ -290,6 +294,7 @@ struct rt_scene {
     CompiledScene compiled;
     uint32_t ops_bytes = 0;
     bool ops_in_global = false;
+    bool fold = false;           // the stream holds cube primitives or instances: the FOLD form of the box-test loop (render_mk.cuh)
 };
 
 static void context_free(rt_context* c) {
@@ -550,9 +555,8 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* v = std::getenv("RT_B200_SLAB_DROP")) c->slab_drop = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("RT_B200_MIN_TRAV")) c->min_trav = std::max(1, std::atoi(v));
 #endif
-    for (int counting = 0; counting < 2; ++counting)
-        for (int in_smem = 0; in_smem < 2; ++in_smem)
-            CU(cudaFuncSetAttribute(mk_kernel(counting != 0, in_smem != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    for (int k = 0; k < 8; ++k)
+        CU(cudaFuncSetAttribute(mk_kernel((k & 1) != 0, (k & 2) != 0, (k & 4) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
 #ifdef RT_B200_DEV
     for (int in_smem = 0; in_smem < 2; ++in_smem)
         CU(cudaFuncSetAttribute(q_kernel(in_smem != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
@@ -637,6 +641,13 @@ int rt_scene_upload_ex(rt_context* c, const rt_scene_desc* desc, uint32_t layout
     UP(cs.precise, precise, const double4*)
 #undef UP
     s->ops_bytes = (uint32_t)(cs.ops.size() * sizeof(F4));
+    for (int i = 0; i < cs.n_world_words;) {   // op by op: payload words can alias a header only by accident of their bits
+        uint32_t hdr;
+        std::memcpy(&hdr, &cs.ops[i].w, 4);
+        const uint32_t kind = hdr_kind(hdr);
+        if (kind == OP_BOX || kind == OP_XFORM_ENTER) { s->fold = true; break; }
+        i += op_words(kind, hdr_flags(hdr));
+    }
     s->dev.n_words = cs.n_world_words;
     s->dev.n_media = (int)cs.hoisted_media.size();
     for (int k = 0; k < s->dev.n_media; ++k) s->dev.media_op[k] = cs.hoisted_media[k];
@@ -808,7 +819,7 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
         if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: per-thread state does not fit in shared memory");
         prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
         CU(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned int), stream));
-        render_fn fn = mk_kernel(counting, in_smem);
+        render_fn fn = mk_kernel(counting, in_smem, s->fold);
         fn<<<c->sm_count, kRenderThreads, lay.total, stream>>>(prm);
     }
     CU(cudaGetLastError());

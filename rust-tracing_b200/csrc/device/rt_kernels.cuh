@@ -608,7 +608,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ops& ops, 
             case 4: outward.y = 1.0f;  h.u = ax;        h.v = 1.0f - az; break;
             default: outward.y = -1.0f; h.u = ax;       h.v = az; break;
         }
-        h.mat = fbits(w1.w);
+        h.mat = fbits(hi.w);
         h.prim = fbits(lo.w) + face;
         h.origin = origin_code(best.op, face);
     } else {  // OP_MEDIUM: HitRecord::new(r.at(t), phase, t, r, r.direction) (constant_medium.rs:52-58)

@@ -199,7 +199,7 @@ struct Compiler {
     // Cull box of `kind` (OP_INNER / OP_XFORM_ENTER: centre / half extent, padded; OP_INNER_REF: the reference's corners);
     // w1.w = skip (a word index until the final pass turns it into a link). Returns the index of word 1.
     int push_box_header(const Box& b, uint32_t kind, int size_words) {
-        const uint32_t hdr = make_hdr(kind, 0, (uint32_t)size_words);
+        const uint32_t hdr = make_hdr(kind, kind == OP_INNER_REF ? FLAG_ALWAYS : 0u, (uint32_t)size_words);
         if (!b.valid) {  // empty subtree: a box nothing can hit (far < near on every axis, whatever the ray)
             const float inf = std::numeric_limits<float>::infinity();
             if (kind == OP_INNER_REF) { push(inf, inf, inf, bits_to_float(hdr)); push(-inf, -inf, -inf, 0.0f); }
@@ -288,9 +288,9 @@ struct Compiler {
             hh[k] = (float)(0.5 * (hi - lo));
         }
         push(cc[0], cc[1], cc[2], bits_to_float(make_hdr(OP_BOX, 0, 4)));
-        push(hh[0], hh[1], hh[2], int_to_float_bits(d->hittables[first].mat));
+        push(hh[0], hh[1], hh[2], 0.0f);   // .w: the fall-through link, written by the final pass
         push((float)h.v0[0], (float)h.v0[1], (float)h.v0[2], int_to_float_bits(first));
-        push((float)h.v1[0], (float)h.v1[1], (float)h.v1[2], 0.0f);
+        push((float)h.v1[0], (float)h.v1[1], (float)h.v1[2], int_to_float_bits(d->hittables[first].mat));
         for (int c = 0; c < 3; ++c) scale = std::fmax(scale, std::fmax(std::fabs(h.v0[c]), std::fabs(h.v1[c])));
     }
 
@@ -368,7 +368,7 @@ struct Compiler {
                 emit(cur, in_boundary);
                 xf_stack.pop_back();
                 const int parent = in_xform() ? xf_stack.back().first : -1;
-                push(int_to_float_bits(parent), 0.0f, 0.0f, bits_to_float(make_hdr(OP_XFORM_EXIT, 0, 2)));
+                push(int_to_float_bits(parent), 0.0f, 0.0f, bits_to_float(make_hdr(OP_XFORM_EXIT, FLAG_ALWAYS, 2)));
                 push(0.0f, 0.0f, 0.0f, 0.0f);
                 patch_skip(w1);
                 break;
@@ -720,6 +720,7 @@ int compile_scene(const rt_scene_desc* desc, const CompileOptions& opt, Compiled
             const uint32_t nh = (hdr & 0x0fffffffu) | (cls_at(ft) << 28);
             std::memcpy(&ops[i].w, &nh, 4);
             if (has_skip) ops[i + 1].w = bits_to_float(make_link(skip, cls_at(skip)));
+            if (kind == OP_BOX) ops[i + 1].w = bits_to_float(make_link(ft, cls_at(ft)));   // a missed cube goes on like a rejected cull box
             i += size;
         }
         if (i != n) { msg = "internal: op stream walk ended off the end"; if (err) *err = msg.c_str(); return RT_ERR_INTERNAL; }
