@@ -82,7 +82,7 @@ constexpr uint32_t CLS_NEED = 6;   // holds no path and wants one; CLS_IDLE: hol
 // Shade the finished segments (renderer.rs:144-153), hand out new paths, start the next segments: hoisted media,
 // per-ray set-up into shared memory. Called by all 32 lanes of the warp; lanes that are mid-traversal pass through.
 // Returns the lane's new link.
-template <bool COUNT, class Ops>
+template <bool COUNT, class Ops, unsigned FEAT>
 __device__ __noinline__ uint32_t shade_phase(uint32_t link, unsigned* cnt) {
     unsigned char* smem = reinterpret_cast<unsigned char*>(dyn_smem);
     const RenderParams& prm = *reinterpret_cast<const RenderParams*>(smem + kSmemParams);
@@ -122,7 +122,7 @@ __device__ __noinline__ uint32_t shade_phase(uint32_t link, unsigned* cnt) {
             HitRec h;
             Best b;
             b.t = COLD(F_BEST_T); b.op = best_op; b.xf = best_xf;
-            finalize_hit(S, ops, ray, b, h);
+            finalize_hit<FEAT>(S, ops, ray, b, h);
             if (COUNT) {
                 if (best_xf >= 0) cnt[K_FINALIZE_XFORM]++;
                 const float4 m0 = __ldg(S.mats + 2 * h.mat);
@@ -233,7 +233,7 @@ __device__ __noinline__ uint32_t shade_phase(uint32_t link, unsigned* cnt) {
         COLD_I(F_XF) = -1;
         Best b;
         b.t = inf; b.op = -1; b.xf = -1;
-        media_prepass(S, ops, so, sd, a, inv_a, COLD(F_TIME), tmin, key, depth, b);
+        media_prepass<FEAT>(S, ops, so, sd, a, inv_a, COLD(F_TIME), tmin, key, depth, b);
         COLD(F_BEST_T) = b.t; COLD_I(F_BEST_OP) = b.op; COLD_I(F_BEST_XF) = -1;
         if (COUNT) cnt[K_MEDIUM] += S.n_media;
         link = prm.first_link;
@@ -266,8 +266,9 @@ __device__ __noinline__ uint32_t medium_phase(uint32_t link) {
     return ((uint32_t)next_word << 4) | ((uint32_t)fbits(w0.w) & 0xf0000000u);
 }
 
-template <bool COUNT, bool OPS_SMEM, bool FOLD>
+template <bool COUNT, bool OPS_SMEM, unsigned FEAT>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const RenderParams prm_in) {
+    constexpr bool FOLD = (FEAT & FEAT_FOLD) != 0u;
     unsigned char* smem = reinterpret_cast<unsigned char*>(dyn_smem);
     const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
     const int tid = threadIdx.x;
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                         CNT(K_SPHERE);
                         if (COUNT) { if ((hdr >> 12) & FLAG_MOVING) cnt[K_SPHERE_MOVING]++; if ((hdr >> 12) & FLAG_PRECISE) cnt[K_SPHERE_PRECISE]++; }
                         float t;
-                        if (sphere_test(S, ops, link, w0, w1, CUR_O(), CUR_D(), COLD(F_A), COLD(F_INVA), COLD(F_TIME), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
+                        if (sphere_test<FEAT>(S, ops, link, w0, w1, CUR_O(), CUR_D(), COLD(F_A), COLD(F_INVA), COLD(F_TIME), tmin, best_t, COLD_I(F_ORIGIN), &t)) {
                             best_t = t; best_op = (int)((link & kLinkMask) >> 4); best_xf = COLD_I(F_XF);
                             CNT(K_SPHERE_HIT);
                         }
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                 if ((link >> 28) == CLS_MEDIUM) {     // a medium that could not be hoisted (inside an instance / generic boundary)
                     CNT(K_MEDIUM);
                     COLD(F_BEST_T) = best_t; COLD_I(F_BEST_OP) = best_op; COLD_I(F_BEST_XF) = best_xf;
-                    link = medium_phase<Ops>(link);
+                    if (FEAT & FEAT_RARE) link = medium_phase<Ops>(link);
                 }
                 const RaySetup R = ray_setup(CUR_O(), CUR_D());      // nothing live across the call (see the shade branch)
                 inv = R.inv; oi = R.oi; eps = R.eps;
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                 // current ray, the op words are fetched again (once per ~25 box tests of every lane: cheap, and it frees the
                 // register allocation of the box-test loop from the needs of the shading code).
                 COLD(F_BEST_T) = best_t; COLD_I(F_BEST_OP) = best_op; COLD_I(F_BEST_XF) = best_xf;
-                link = shade_phase<COUNT, Ops>(link, cnt);
+                link = shade_phase<COUNT, Ops, FEAT>(link, cnt);
                 const RaySetup R = ray_setup(CUR_O(), CUR_D());
                 inv = R.inv; oi = R.oi; eps = R.eps;
                 best_t = COLD(F_BEST_T); best_op = COLD_I(F_BEST_OP); best_xf = COLD_I(F_BEST_XF);
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
             // side takes the rare branch. Three more instructions per repetition, so scenes without such ops go without.
             const bool rare = in_class && (hdr & kHdrNotInner) != 0u && (!FOLD || pass || (hdr & kHdrAlwaysRare) != 0u);
             if (COUNT && FOLD && in_class && (hdr & kHdrNotInner) != 0u && !rare) CNT(((hdr >> 8) & 15u) == OP_BOX ? K_BOX : K_SLAB);
-            if (rare) {
+            if (__builtin_expect(rare, 0)) {   // placed out of line: the common repetition stays one straight run of instructions
                 const uint32_t kind = (hdr >> 8) & 15u;
                 const uint32_t ft = link + (hdr & kHdrFallThrough);
                 nl = ft;
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                     COLD_I(F_XF) = parent;
                 } else {
                     CNT(K_SLAB);
-                    nl = aabb_hit_reference(w0, w1, CUR_O(), inv, tmin, best_t) ? ft : (uint32_t)fbits(w1.w);
+                    if (FEAT & FEAT_RARE) nl = aabb_hit_reference(w0, w1, CUR_O(), inv, tmin, best_t) ? ft : (uint32_t)fbits(w1.w);
                 }
             } else if (COUNT && in_class) {
                 CNT(K_SLAB);

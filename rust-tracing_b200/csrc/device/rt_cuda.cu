@@ -234,14 +234,46 @@ DevCamera make_dev_camera(const rt_camera_desc& c) {
 
 }  // namespace
 
-typedef void (*render_fn)(const RenderParams);
-static render_fn mk_kernel(bool counting, bool ops_smem, bool fold) {
-    if (fold) {
-        if (counting) return ops_smem ? render_kernel_mk<true, true, true> : render_kernel_mk<true, false, true>;
-        return ops_smem ? render_kernel_mk<false, true, true> : render_kernel_mk<false, false, true>;
+// FEAT_* bits of a compiled scene: walks the world program op by op (payload words can alias a header only by accident
+// of their bits) and the hoisted medium bodies.
+static unsigned scene_features(const CompiledScene& cs) {
+    unsigned feat = 0;
+    auto hdr_at = [&](int i) { uint32_t h; std::memcpy(&h, &cs.ops[i].w, 4); return h; };
+    auto bits = [&](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
+    auto medium = [&](int i) {
+        const uint32_t flags = hdr_flags(hdr_at(i));
+        if ((int)flags == MEDIUM_BOUNDARY_PROGRAM) feat |= FEAT_RARE;
+        if ((int)flags == MEDIUM_BOUNDARY_SPHERE && ((bits(cs.ops[i + 2].w) >> 24) & FLAG_PRECISE)) feat |= FEAT_PRECISE;
+    };
+    for (int i = 0; i < cs.n_world_words;) {
+        const uint32_t hdr = hdr_at(i), kind = hdr_kind(hdr), flags = hdr_flags(hdr);
+        if (kind == OP_BOX || kind == OP_XFORM_ENTER) feat |= FEAT_FOLD;
+        if (kind == OP_SPHERE && (flags & FLAG_PRECISE)) feat |= FEAT_PRECISE;
+        if (kind == OP_INNER_REF) feat |= FEAT_RARE;
+        if (kind == OP_MEDIUM) { feat |= FEAT_RARE; medium(i); }
+        i += op_words(kind, flags);
     }
-    if (counting) return ops_smem ? render_kernel_mk<true, true, false> : render_kernel_mk<true, false, false>;
-    return ops_smem ? render_kernel_mk<false, true, false> : render_kernel_mk<false, false, false>;
+    for (int32_t m : cs.hoisted_media) medium(m);
+    return feat;
+}
+
+typedef void (*render_fn)(const RenderParams);
+// The render kernel is specialised on what the scene holds (FEAT_*, rt_kernels.cuh): the instantiation that renders a scene
+// carries no code the scene cannot reach (the kernel is bound by instruction fetch: profiles/r2_k1_icache.md). The
+// instrumented build and the global-memory fallback exist in the generic form only.
+static render_fn mk_kernel(bool counting, bool ops_smem, unsigned feat) {
+    if (counting) return ops_smem ? render_kernel_mk<true, true, FEAT_ALL> : render_kernel_mk<true, false, FEAT_ALL>;
+    if (!ops_smem) return render_kernel_mk<false, false, FEAT_ALL>;
+    switch (feat & FEAT_ALL) {
+        case 0u: return render_kernel_mk<false, true, 0u>;
+        case 1u: return render_kernel_mk<false, true, 1u>;
+        case 2u: return render_kernel_mk<false, true, 2u>;
+        case 3u: return render_kernel_mk<false, true, 3u>;
+        case 4u: return render_kernel_mk<false, true, 4u>;
+        case 5u: return render_kernel_mk<false, true, 5u>;
+        case 6u: return render_kernel_mk<false, true, 6u>;
+        default: return render_kernel_mk<false, true, 7u>;
+    }
 }
 
 #ifdef RT_B200_DEV
@@ -294,7 +326,7 @@ struct rt_scene {
     CompiledScene compiled;
     uint32_t ops_bytes = 0;
     bool ops_in_global = false;
-    bool fold = false;           // the stream holds cube primitives or instances: the FOLD form of the box-test loop (render_mk.cuh)
+    unsigned features = 0;       // FEAT_* the stream needs: picks the render kernel's instantiation
 };
 
 static void context_free(rt_context* c) {
@@ -555,8 +587,9 @@ int rt_context_create(int device_id, rt_context** out) {
     if (const char* v = std::getenv("RT_B200_SLAB_DROP")) c->slab_drop = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("RT_B200_MIN_TRAV")) c->min_trav = std::max(1, std::atoi(v));
 #endif
-    for (int k = 0; k < 8; ++k)
-        CU(cudaFuncSetAttribute(mk_kernel((k & 1) != 0, (k & 2) != 0, (k & 4) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    for (int k = 0; k < 4; ++k)
+        for (unsigned feat = 0; feat <= FEAT_ALL; ++feat)
+            CU(cudaFuncSetAttribute(mk_kernel((k & 1) != 0, (k & 2) != 0, feat), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
 #ifdef RT_B200_DEV
     for (int in_smem = 0; in_smem < 2; ++in_smem)
         CU(cudaFuncSetAttribute(q_kernel(in_smem != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
@@ -641,13 +674,7 @@ int rt_scene_upload_ex(rt_context* c, const rt_scene_desc* desc, uint32_t layout
     UP(cs.precise, precise, const double4*)
 #undef UP
     s->ops_bytes = (uint32_t)(cs.ops.size() * sizeof(F4));
-    for (int i = 0; i < cs.n_world_words;) {   // op by op: payload words can alias a header only by accident of their bits
-        uint32_t hdr;
-        std::memcpy(&hdr, &cs.ops[i].w, 4);
-        const uint32_t kind = hdr_kind(hdr);
-        if (kind == OP_BOX || kind == OP_XFORM_ENTER) { s->fold = true; break; }
-        i += op_words(kind, hdr_flags(hdr));
-    }
+    s->features = scene_features(cs);
     s->dev.n_words = cs.n_world_words;
     s->dev.n_media = (int)cs.hoisted_media.size();
     for (int k = 0; k < s->dev.n_media; ++k) s->dev.media_op[k] = cs.hoisted_media[k];
@@ -819,7 +846,7 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
         if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: per-thread state does not fit in shared memory");
         prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
         CU(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned int), stream));
-        render_fn fn = mk_kernel(counting, in_smem, s->fold);
+        render_fn fn = mk_kernel(counting, in_smem, s->features);
         fn<<<c->sm_count, kRenderThreads, lay.total, stream>>>(prm);
     }
     CU(cudaGetLastError());

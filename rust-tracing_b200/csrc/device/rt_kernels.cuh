@@ -133,6 +133,13 @@ struct Ray {
     float time;
 };
 
+// Features of a scene the render kernel is specialised on (render_mk.cuh): code a scene cannot reach is not compiled into
+// the instantiation that renders it. The parity kernels and the generic instantiation carry everything.
+constexpr unsigned FEAT_FOLD = 1u;      // cube primitives or instances in the stream: FOLD form of the box-test loop
+constexpr unsigned FEAT_PRECISE = 2u;   // an f64 sphere (radius > 200) as a primitive or as a medium boundary
+constexpr unsigned FEAT_RARE = 4u;      // media in the stream / boundary programs / OP_INNER_REF
+constexpr unsigned FEAT_ALL = 7u;
+
 struct Best {
     float t;
     int op;   // word index of the winning primitive / medium op, -1 = none
@@ -296,14 +303,14 @@ __device__ __noinline__ bool sphere_roots_f64(float3 o, float3 d, float time, co
 // ---- primitive tests. Each returns true and the accepted parameter when the op wins over the current best ----
 
 // Sphere::hit (sphere.rs:59-89). w2 (center_vec) is fetched only for a moving sphere.
-template <class Ops>
+template <unsigned FEAT = FEAT_ALL, class Ops>
 __device__ __forceinline__ bool sphere_test(const DevScene& S, const Ops& ops, uint32_t link, float4 w0, float4 w1, float3 o, float3 d,
                                             float a, float inv_a, float time, float tmin, float tmax, int origin, float* t_out) {
     const uint32_t flags = ((uint32_t)fbits(w0.w) >> 12) & 15u;
     const bool self_origin = starts_on(origin, link);
     float r1, r2;
     bool ok;
-    if (flags & FLAG_PRECISE) {
+    if ((FEAT & FEAT_PRECISE) && (flags & FLAG_PRECISE)) {
         ok = sphere_roots_f64(o, d, time, S.precise + 2 * fbits(w1.w), flags & FLAG_MOVING, self_origin, &r1, &r2);
     } else {
         float3 c = f3(w0);
@@ -374,18 +381,18 @@ __device__ float boundary_closest_t(const DevScene& S, const Ops& ops, int begin
 
 // ConstantMedium::hit (constant_medium.rs:34-70); the medium's box was tested by the preceding OP_INNER.
 // `at` = byte offset of the op. Returns true and the scatter parameter when the medium wins; *next_word = the op after it.
-template <class Ops>
+template <unsigned FEAT = FEAT_ALL, class Ops>
 __device__ __forceinline__ bool medium_test(const DevScene& S, const Ops& ops, uint32_t at, float4 w0, float4 w1, float3 o, float3 d,
                                             float a, float inv_a, float time, float tmin, float tmax, uint4 key, uint32_t seg,
                                             float* t_out, int* next_word) {
     const int bkind = (int)(((uint32_t)fbits(w0.w) >> 12) & 15u);
     const float4 w2 = ops(at + 32u);
-    float t1, t2;
-    bool ok;
+    float t1 = 0.0f, t2 = 0.0f;
+    bool ok = false;
     if (bkind == MEDIUM_BOUNDARY_SPHERE) {
         const uint32_t aux = (uint32_t)fbits(w2.w);
         const bool moving = (aux >> 24) & FLAG_MOVING;
-        if ((aux >> 24) & FLAG_PRECISE) {
+        if ((FEAT & FEAT_PRECISE) && ((aux >> 24) & FLAG_PRECISE)) {
             ok = sphere_roots_f64(o, d, time, S.precise + 2 * (aux & 0xffffffu), moving, false, &t1, &t2);
         } else {
             float3 c = f3(w1);
@@ -403,7 +410,7 @@ __device__ __forceinline__ bool medium_test(const DevScene& S, const Ops& ops, u
         const float inf = __int_as_float(0x7f800000);
         ok = (t1 <= t2) && (t2 >= t1 + 0.0001f) && fabsf(t1) < inf && fabsf(t2) < inf;   // hit2: closed interval from hit1.t + 0.0001
         *next_word = (int)(at >> 4) + 5;
-    } else {
+    } else if (FEAT & FEAT_RARE) {
         Ray lr; lr.o = o; lr.d = d; lr.time = time;
         const float inf = __int_as_float(0x7f800000);
         t1 = boundary_closest_t(S, ops, fbits(w1.x), fbits(w1.y), lr, -inf, inf);
@@ -425,14 +432,14 @@ __device__ __forceinline__ bool medium_test(const DevScene& S, const Ops& ops, u
 }
 
 // Hoisted (world-space) media: evaluated before the traversal of every segment; each may lower best.t.
-template <class Ops>
+template <unsigned FEAT = FEAT_ALL, class Ops>
 __device__ __forceinline__ void media_prepass(const DevScene& S, const Ops& ops, float3 o, float3 d, float a, float inv_a, float time,
                                               float tmin, uint4 key, uint32_t seg, Best& best) {
     for (int m = 0; m < S.n_media; ++m) {
         const uint32_t at = (uint32_t)S.media_op[m] << 4;
         float t;
         int next;
-        if (medium_test(S, ops, at, ops(at), ops(at + 16u), o, d, a, inv_a, time, tmin, best.t, key, seg, &t, &next)) {
+        if (medium_test<FEAT>(S, ops, at, ops(at), ops(at + 16u), o, d, a, inv_a, time, tmin, best.t, key, seg, &t, &next)) {
             best.t = t; best.op = S.media_op[m]; best.xf = -1;
         }
     }
@@ -538,7 +545,7 @@ __device__ __noinline__ float3 precise_sphere_normal(const double4* pr, bool mov
               (float)((((double)o.z - cz) + (double)t * (double)d.z) * inv_r));
 }
 
-template <class Ops>
+template <unsigned FEAT = FEAT_ALL, class Ops>
 __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ops& ops, const Ray& ray, const Best& best, HitRec& h) {
     float3 o = ray.o, d = ray.d;
     float4 x2, x3;
@@ -559,7 +566,7 @@ __device__ __forceinline__ void finalize_hit(const DevScene& S, const Ops& ops, 
     if (kind == OP_SPHERE) {
         const uint32_t flags = (hdr >> 12) & 15u;
         const float3 pl = fma3(t, d, o);
-        if (flags & FLAG_PRECISE) {
+        if ((FEAT & FEAT_PRECISE) && (flags & FLAG_PRECISE)) {
             outward = precise_sphere_normal(S.precise + 2 * fbits(w1.w), flags & FLAG_MOVING, o, d, t, ray.time);
         } else {
             float3 c = f3(w0);
@@ -689,7 +696,7 @@ __device__ __forceinline__ float perlin_turbulence(const DevScene& S, const Perl
 
 // Texture::value (texture.rs:12-14). One out-of-line copy: it is called once per shaded hit, and keeping it (and
 // the Perlin code behind it) out of the render loop's body keeps the loop's instruction footprint small.
-__device__ __noinline__ float3 texture_value(const DevScene& S, const PerlinShared& P, int tex, float3 p, float u, float v,
+__device__ __noinline__ float3 texture_value(const DevScene& S, const PerlinShared P, int tex, float3 p, float u, float v,
                                              bool uv_lazy, float3 sn) {
     const float4* __restrict__ T = S.texs;
     for (int guard = 0; guard < 16; ++guard) {

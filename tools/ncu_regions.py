@@ -67,12 +67,14 @@ def function_table(src_text):
 # labelled line patterns of the render loop: first match wins, searched on the source TEXT of the line's region start
 LOOP_MARKS = [
     ("vote", r"// ---- the vote|const unsigned n_slab = __popc|unsigned n_slab = __popc"),
-    ("slab loop", r"if \(pick == CLS_SLAB\)"),
-    ("sphere class", r"else if \(pick == CLS_SPHERE\)"),
+    ("slab loop: rare kinds (cube accept, instance enter / exit)", r"^\s*if \(rare\) \{"),
+    ("slab loop", r"if \(pick == CLS_SLAB\)|// ---- cull boxes|link = in_class \? nl : link"),
+    ("sphere class", r"if \(pick == CLS_SPHERE\)"),
     ("quad class", r"else if \(pick == CLS_QUAD\)"),
     ("medium class", r"else if \(pick == CLS_MEDIUM\)"),
     ("box class", r"else if \(pick == CLS_BOX\)"),
     ("shade call / hand-over", r"// ---- shade"),
+    ("entry into the box-test loop after another class", r"if \(n_slab < \(unsigned\)slab_fast\) continue"),
     ("epilogue", r"#undef CNT"),
 ]
 
