@@ -17,7 +17,18 @@
 //    FMA-pipe instructions and two 3-input min/max, with no per-node sign selects;
 //  * the cursor is a link (byte offset | class << 28) and the header of a cull box IS its fall-through increment: the
 //    successor of a box test is one add and one select, "am I at a box" one unsigned compare;
-//  * the repetition loop ends with one ballot + popc + compare (no repetition counter);
+//  * the repetition loop ends with one ballot + popc + compare (no repetition counter), and its body has no divergent
+//    branch in the common case: EVERY lane runs the box arithmetic on the op words it holds (lanes of other classes keep
+//    their link, the fetch is a predicated LDS), so a repetition is one straight run of ~37 instructions instead of a
+//    branch around the body with its reconvergence pair (+5%);
+//  * FOLD (scenes with cube primitives / instances): such an op whose box the ray MISSES is finished by the same arithmetic
+//    (its second word ends with the link to follow), only the accepting side enters the rare-kind branch: 21% of the
+//    repetitions instead of 70% (+6% final_scene; three more instructions per repetition, so it is a template parameter);
+//  * the loop's top is the full vote; after another class has run the box-test loop is entered directly when enough lanes
+//    stand at boxes, and it hands its last lane count to the next vote (no second ballot, no jump table: +4..7%);
+//  * the kernel is specialised on what the scene holds (FEAT_*): f64 spheres, in-stream media / boundary programs and
+//    reference boxes are compiled out of the instantiation that renders a scene without them (5 424 -> 2 928 instructions
+//    for final_scene, +6%; the kernel is bound by instruction fetch, profiles/r2_k1_icache.md);
 //  * shading, path regeneration and segment start are ONE out-of-line function (shade_phase): its register needs no
 //    longer decide what the traversal loop may keep in registers (the inlined form spilled the loop's own per-ray
 //    constants and reloaded them in every repetition). Everything the two sides share lives in shared memory;
@@ -437,9 +448,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
             // FOLD (scenes with cube primitives or instances): a cube or an instance whose box the ray misses is finished
             // by the arithmetic above - their second word ends with the link to follow then - and only the accepting
             // side takes the rare branch. Three more instructions per repetition, so scenes without such ops go without.
-            const bool rare = in_class && (hdr & kHdrNotInner) != 0u && (!FOLD || pass || (hdr & kHdrAlwaysRare) != 0u);
-            if (COUNT && FOLD && in_class && (hdr & kHdrNotInner) != 0u && !rare) CNT(((hdr >> 8) & 15u) == OP_BOX ? K_BOX : K_SLAB);
-            if (__builtin_expect(rare, 0)) {   // placed out of line: the common repetition stays one straight run of instructions
+            const bool rare = (FEAT & (FEAT_FOLD | FEAT_RARE)) != 0u &&      // a stream without either holds nothing but OP_INNER here
+                              in_class && (hdr & kHdrNotInner) != 0u && (!FOLD || pass || (hdr & kHdrAlwaysRare) != 0u);
+            if (rare) {
                 const uint32_t kind = (hdr >> 8) & 15u;
                 const uint32_t ft = link + (hdr & kHdrFallThrough);
                 nl = ft;
@@ -485,8 +496,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                     CNT(K_SLAB);
                     if (FEAT & FEAT_RARE) nl = aabb_hit_reference(w0, w1, CUR_O(), inv, tmin, best_t) ? ft : (uint32_t)fbits(w1.w);
                 }
-            } else if (COUNT && in_class) {
-                CNT(K_SLAB);
+            } else if (COUNT && in_class) {   // OP_INNER, or a cube / instance finished by the fold
+                CNT((hdr & kHdrNotInner) != 0u && ((hdr >> 8) & 15u) == OP_BOX ? K_BOX : K_SLAB);
             }
             link = in_class ? nl : link;
             if (OPS_SMEM) {   // predicated loads (the compiler would branch around them): lanes of other classes keep their words
