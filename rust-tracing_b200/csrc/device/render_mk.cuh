@@ -43,7 +43,7 @@
 #ifdef RT_OPT_THREADS
 constexpr int kRenderThreads = RT_OPT_THREADS;
 #else
-constexpr int kRenderThreads = 768;   // 24 warps: one CTA per SM (80 registers per thread)
+constexpr int kRenderThreads = 896;   // 28 warps: one CTA per SM (72 registers per thread; 768 / 80: -4..6%, profiles/r2_ab15*)
 #endif
 constexpr int kRenderWarps = kRenderThreads / 32;
 
@@ -210,7 +210,7 @@ __device__ __noinline__ uint32_t shade_phase(uint32_t link, unsigned* cnt) {
                 const int pix = py * C.width + px;                       // renderer.rs:32-33
                 const uint32_t sample = (uint32_t)(prm.sample_begin + pool[W_SAMPLE0] + sv);
                 key = path_key(prm.seed, (uint32_t)pix, sample);
-                const Ray ray = camera_ray(C, px, py, key);
+                const Ray ray = camera_ray<(FEAT & FEAT_DEFOCUS) != 0u>(C, px, py, key);
                 COLD(F_WO) = ray.o.x; COLD(F_WO + 1) = ray.o.y; COLD(F_WO + 2) = ray.o.z;
                 COLD(F_WD) = ray.d.x; COLD(F_WD + 1) = ray.d.y; COLD(F_WD + 2) = ray.d.z;
                 COLD(F_L) = 0.0f; COLD(F_L + 1) = 0.0f; COLD(F_L + 2) = 0.0f;

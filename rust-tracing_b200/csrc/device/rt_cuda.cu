@@ -23,6 +23,7 @@
 #include <cstring>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 using namespace rtdev;
@@ -243,6 +244,7 @@ static unsigned scene_features(const CompiledScene& cs) {
     auto medium = [&](int i) {
         const uint32_t flags = hdr_flags(hdr_at(i));
         if ((int)flags == MEDIUM_BOUNDARY_PROGRAM) feat |= FEAT_RARE;
+        if ((int)flags == MEDIUM_BOUNDARY_XBOX) feat |= FEAT_XBOX;
         if ((int)flags == MEDIUM_BOUNDARY_SPHERE && ((bits(cs.ops[i + 2].w) >> 24) & FLAG_PRECISE)) feat |= FEAT_PRECISE;
     };
     for (int i = 0; i < cs.n_world_words;) {
@@ -261,19 +263,15 @@ typedef void (*render_fn)(const RenderParams);
 // The render kernel is specialised on what the scene holds (FEAT_*, rt_kernels.cuh): the instantiation that renders a scene
 // carries no code the scene cannot reach (the kernel is bound by instruction fetch: profiles/r2_k1_icache.md). The
 // instrumented build and the global-memory fallback exist in the generic form only.
+template <unsigned... F>
+static render_fn mk_specialised(unsigned feat, std::integer_sequence<unsigned, F...>) {
+    static const render_fn table[] = {render_kernel_mk<false, true, F>...};
+    return table[feat];
+}
 static render_fn mk_kernel(bool counting, bool ops_smem, unsigned feat) {
     if (counting) return ops_smem ? render_kernel_mk<true, true, FEAT_ALL> : render_kernel_mk<true, false, FEAT_ALL>;
     if (!ops_smem) return render_kernel_mk<false, false, FEAT_ALL>;
-    switch (feat & FEAT_ALL) {
-        case 0u: return render_kernel_mk<false, true, 0u>;
-        case 1u: return render_kernel_mk<false, true, 1u>;
-        case 2u: return render_kernel_mk<false, true, 2u>;
-        case 3u: return render_kernel_mk<false, true, 3u>;
-        case 4u: return render_kernel_mk<false, true, 4u>;
-        case 5u: return render_kernel_mk<false, true, 5u>;
-        case 6u: return render_kernel_mk<false, true, 6u>;
-        default: return render_kernel_mk<false, true, 7u>;
-    }
+    return mk_specialised(feat & FEAT_ALL, std::make_integer_sequence<unsigned, FEAT_ALL + 1u>{});
 }
 
 #ifdef RT_B200_DEV
@@ -846,7 +844,7 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
         if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: per-thread state does not fit in shared memory");
         prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
         CU(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned int), stream));
-        render_fn fn = mk_kernel(counting, in_smem, s->features);
+        render_fn fn = mk_kernel(counting, in_smem, s->features | (prm.cam.defocus ? FEAT_DEFOCUS : 0u));
         fn<<<c->sm_count, kRenderThreads, lay.total, stream>>>(prm);
     }
     CU(cudaGetLastError());

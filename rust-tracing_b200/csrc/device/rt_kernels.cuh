@@ -138,7 +138,9 @@ struct Ray {
 constexpr unsigned FEAT_FOLD = 1u;      // cube primitives or instances in the stream: FOLD form of the box-test loop
 constexpr unsigned FEAT_PRECISE = 2u;   // an f64 sphere (radius > 200) as a primitive or as a medium boundary
 constexpr unsigned FEAT_RARE = 4u;      // media in the stream / boundary programs / OP_INNER_REF
-constexpr unsigned FEAT_ALL = 7u;
+constexpr unsigned FEAT_XBOX = 8u;      // a medium bounded by a (rotated, translated) cube
+constexpr unsigned FEAT_DEFOCUS = 16u;  // the camera has a defocus disk (a property of the launch, not of the scene)
+constexpr unsigned FEAT_ALL = 31u;
 
 struct Best {
     float t;
@@ -402,7 +404,7 @@ __device__ __forceinline__ bool medium_test(const DevScene& S, const Ops& ops, u
         // hit1 over the universe takes the near root; hit2 needs a root > hit1.t + 0.0001
         ok = ok && (t2 > t1 + 0.0001f);
         *next_word = (int)(at >> 4) + 3;
-    } else if (bkind == MEDIUM_BOUNDARY_XBOX) {
+    } else if ((FEAT & FEAT_XBOX) && bkind == MEDIUM_BOUNDARY_XBOX) {
         // both boundary hits of a (rotated, translated) cube from one slab test in the cube's frame
         const float4 lo = ops(at + 48u), hi = ops(at + 64u);
         const float3 lo_ = xform_point(o, w1, w2), ld_ = xform_dir(d, w1, w2);
@@ -783,6 +785,7 @@ __device__ __forceinline__ bool shade(const DevScene& S, const PerlinShared& P, 
 }
 
 // ------------------------------------------------------------------ camera
+template <bool DEFOCUS = true>
 __device__ __forceinline__ Ray camera_ray(const DevCamera& C, int px, int py, uint4 key) {   // camera.rs:112-137
     const uint4 r = draw(key, 0u, P_CAMERA);
     const float sx = (float)px + (-0.5f + u01(r.x));
@@ -790,7 +793,7 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera& C, int px, int py, ui
     float3 rel = fma3(sy, C.dv, fma3(sx, C.du, C.rel00));   // pixel_sample - center
     Ray ray;
     ray.o = C.center;
-    if (C.defocus) {
+    if (DEFOCUS && C.defocus) {
         const uint4 e = draw(key, 0u, P_CAMERA_DISK);
         const float rad = sqrtf(u01(e.x));
         float s, c;
