@@ -408,9 +408,11 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel_mk(const Rend
                     if (!__any_sync(0xffffffffu, (link >> 28) == CLS_QUAD)) break;
                 }
             } else if (pick == CLS_MEDIUM) {
+                // EVERY lane parks its closest hit (as in the shade branch): all of them reload it below, and a lane of
+                // another class that reloaded a stale value would forget the hits it has found in this segment
+                COLD(F_BEST_T) = best_t; COLD_I(F_BEST_OP) = best_op; COLD_I(F_BEST_XF) = best_xf;
                 if ((link >> 28) == CLS_MEDIUM) {     // a medium that could not be hoisted (inside an instance / generic boundary)
                     CNT(K_MEDIUM);
-                    COLD(F_BEST_T) = best_t; COLD_I(F_BEST_OP) = best_op; COLD_I(F_BEST_XF) = best_xf;
                     if (FEAT & FEAT_RARE) link = medium_phase<Ops>(link);
                 }
                 const RaySetup R = ray_setup(CUR_O(), CUR_D());      // nothing live across the call (see the shade branch)
