@@ -327,6 +327,26 @@ def test_hit_parity_one_million_rays(rt, ob, ctx, earth, idx):
     ds.close()
 
 
+@pytest.mark.parametrize("seed", [2, 9, 11, 14, 24, 36])
+def test_hit_parity_rich_scenes(rt, ob, ctx, seed):
+    """tools/fuzz_scenes.py::rich_scene: media inside instances, instances inside the boundary of an instanced medium, a
+    2600-sphere BVH (9), reference boxes next to media (24), a 1000-unit ground sphere, fog around everything."""
+    from fuzz_scenes import rich_scene
+    s = rich_scene(5000 + seed)
+    ds = ctx.upload(s)
+    rng = np.random.default_rng(seed)
+    n = 1 << 15
+    rays = np.zeros(n, dtype=rt._abi.ray_dtype())
+    rays["origin"] = rng.uniform(-14, 14, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.5, 2, (n, 1))
+    rays["time"] = rng.random(n)
+    ref = ob.hit_batch(s.desc, rays, seed=seed)
+    dev = ctx.hit_batch(ds, rays, seed=seed)
+    check_hits(dev, ref, rays, max_inequivalent=6)
+    ds.close()
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_hit_parity_random_scenes(rt, ob, ctx, seed):
     """Generated scenes (tools/fuzz_scenes.py): quads with arbitrary edge vectors, nested BVHs, instances, media. A quad

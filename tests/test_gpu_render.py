@@ -245,6 +245,27 @@ def test_generated_scenes_through_the_render_kernel(rt, ob, ctx, seed):
     assert dev[..., :3].mean() == pytest.approx(ref.mean(), rel=2e-3)
 
 
+@pytest.mark.parametrize("seed", [0, 2, 6, 9, 11, 14, 16, 24])
+def test_rich_generated_scenes_through_the_render_kernel(rt, ob, ctx, seed):
+    """tools/fuzz_scenes.py::rich_scene against the oracle, path by path: textured media, media inside instances, instances
+    inside the boundary of an instanced medium (2, 11, 14, 16), reference boxes next to media (24: no hoisting), a 1000-unit
+    ground sphere and a camera-enclosing fog sphere, six NoiseTextures, and (9) a 2600-sphere BVH whose op stream does not
+    fit in shared memory, so the render kernel reads it from global memory."""
+    sys_path_tools()
+    from fuzz_scenes import rich_scene
+    s = rich_scene(5000 + seed)
+    cam = fuzz_camera(rt, seed)
+    if seed == 9:
+        assert rt.scene_layout(s)["n_words"] * 16 > 120 * 1024
+    ds = ctx.upload(s)
+    dev = ctx.render(ds, cam, 0, 4, seed=seed)
+    ds.close()
+    ref, _ = ob.render(s.desc, cam, 0, 4, seed=seed, mode=0)
+    assert np.all(dev[..., 3] == 4) and np.isfinite(dev).all()
+    assert agreement(dev, ref, 4) >= 0.99
+    assert dev[..., :3].mean() == pytest.approx(ref.mean(), rel=2e-3)
+
+
 def sys_path_tools():
     import sys
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")

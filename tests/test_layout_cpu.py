@@ -122,16 +122,47 @@ def test_unsupported_nesting_rejected_on_the_host(rt):
     with pytest.raises(rt._abi.RtError) as e2:
         rt.scene_layout(s2)
     assert e2.value.status == rt._abi.RT_ERR_UNSUPPORTED
+
+
+def test_instances_inside_the_boundary_of_an_instanced_medium(rt, ob):
+    """A generic boundary (list / BVH) that holds instances, around a medium that itself sits inside an instance: the
+    boundary program runs on the enclosing instance's local ray, so its own instances compose their transforms from the
+    program's frame and their exits name parents inside the program only (-1 = the ray the program was handed)."""
+    import opstream
     s3 = rt.Scene()
     m3 = s3.Lambertian(s3.SolidColor(0.5, 0.5, 0.5))
     two = rt.HittableList()
-    two.add(s3.Translate(s3.Sphere((0, 0, 0), 1.0, m3), (1, 0, 0)))
+    two.add(s3.Translate(s3.RotateY(s3.Sphere((0, 0, 0), 1.0, m3), 30.0), (1, 0, 0)))
     two.add(s3.Sphere((0, 2, 0), 1.0, m3))
-    med = s3.ConstantMedium(s3.List(two), 0.5, (1, 1, 1))          # generic boundary holding an instance ...
-    s3.finish(s3.RotateY(med, 20.0))                               # ... inside an instance: the boundary program's rays are local
-    with pytest.raises(rt._abi.RtError) as e3:
-        rt.scene_layout(s3)
-    assert e3.value.status == rt._abi.RT_ERR_UNSUPPORTED
+    nested = rt.HittableList()
+    nested.add(s3.Translate(s3.List(two), (0, 0, 1)))              # an instance holding an instance, all inside the boundary
+    med = s3.ConstantMedium(s3.List(nested), 0.5, (1, 1, 1))
+    s3.finish(s3.Translate(s3.RotateY(med, 20.0), (0.5, 0, 0)))
+    L = rt.scene_layout(s3)
+    assert L["n_medium_in_stream"] == 1 and L["n_xform"] == 3
+    S = opstream.Stream(rt.scene_ops(s3))
+    I = S.i
+    prog = [i for i, k, fl in S.walk() if k == opstream.OP_MEDIUM][0]
+    b0, b1 = int(I[prog + 1, 0]), int(I[prog + 1, 1])
+    exits = [(i, int(I[i, 0])) for i, k, _ in S.walk() if k == opstream.OP_XFORM_EXIT]    # walk() steps through the program too
+    inside = [p for i, p in exits if b0 <= i < b1]
+    outside = [p for i, p in exits if not b0 <= i < b1]
+    assert outside == [-1]                                          # the world program sees only the outer instance
+    # inside the program: the nested instance names its parent IN the program, that parent names the program's own frame
+    assert len(inside) == 2 and b0 <= inside[0] < b1 and inside[1] == -1
+    rng = np.random.default_rng(4)
+    n = 1 << 13
+    rays = np.zeros(n, dtype=rt._abi.ray_dtype())
+    rays["origin"] = rng.uniform(-4, 4, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.5, 2, (n, 1))
+    rays["time"] = rng.random(n)
+    ref = ob.hit_batch(s3.desc, rays, seed=2)
+    emu = opstream.hit_batch(S, rays, seed=2)
+    assert int(ref["hit"].sum()) > 80
+    assert int((emu["hit"] != ref["hit"]).sum()) <= 1
+    both = (emu["hit"] == 1) & (ref["hit"] == 1)
+    assert np.abs(emu["t"] - ref["t"])[both].max() <= 2e-5 * max(1.0, np.abs(ref["t"][both]).max())
 
 
 @pytest.mark.parametrize("idx", range(9))

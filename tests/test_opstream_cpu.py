@@ -64,6 +64,24 @@ def test_stream_walk_matches_oracle_random_scenes(rt, ob, seed):
     compare(opstream.hit_batch(S, rays, seed=seed), ob.hit_batch(s.desc, rays, seed=seed), max_flips=1)
 
 
+RICH_SEEDS = [0, 1, 2, 5, 6, 11, 12, 14, 16, 18, 20, 21, 23, 24, 26, 36]
+
+
+@pytest.mark.parametrize("seed", RICH_SEEDS)
+def test_stream_walk_matches_oracle_rich_scenes(rt, ob, seed):
+    """tools/fuzz_scenes.py::rich_scene: textured media, media inside instances and inside instanced groups (sphere, moving
+    sphere, rotated cube and - seeds 2, 3, 11, 14, 16, 20, 23 - a rotated cube or an instanced group as the boundary of a
+    medium that itself sits inside an instance: the boundary program then composes its instances from its own frame), a
+    1000-unit ground sphere, a fog sphere around everything. Seed 24: a skewed quad under reference boxes (OP_INNER_REF) next
+    to world-space media - what the reference's per-axis box test lets through depends on how far the interval has been
+    narrowed when the node is reached, so such a scene keeps its media at their place in the stream (no hoisting)."""
+    from fuzz_scenes import rich_scene
+    s = rich_scene(5000 + seed)
+    S = opstream.Stream(rt.scene_ops(s))
+    rays = random_rays(rt, np.random.default_rng(seed), 1 << 13)
+    compare(opstream.hit_batch(S, rays, seed=seed), ob.hit_batch(s.desc, rays, seed=seed), max_flips=1)
+
+
 def test_reference_nodes_decide_what_a_skewed_quad_shows(rt, ob):
     """One skewed quad in a BVH: the reference culls the part outside its diagonal box (mostly - the per-axis test lets
     some of it through). The stream must reproduce the oracle exactly; a tight, geometrically complete box would not."""

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import rust_tracing_b200 as rt  # noqa: E402
 from oracle import binding as ob  # noqa: E402
 from test_gpu_hits import check_hits  # noqa: E402
-from fuzz_scenes import random_scene  # noqa: E402
+from fuzz_scenes import random_scene, rich_scene  # noqa: E402
 
 
 def main():
@@ -22,12 +22,19 @@ def main():
     ap.add_argument("--seeds", type=int, default=20)
     ap.add_argument("--rays", type=int, default=1 << 16)
     ap.add_argument("--first", type=int, default=0)
+    ap.add_argument("--rich", action="store_true", help="fuzz_scenes.rich_scene: textures, f64 spheres, media in instances, big streams")
     a = ap.parse_args()
     ctx = rt.Context(0)
     bad = 0
     for seed in range(a.first, a.first + a.seeds):
-        s = random_scene(1000 + seed)
-        ds = ctx.upload(s)
+        try:
+            s = rich_scene(5000 + seed) if a.rich else random_scene(1000 + seed)
+            ds = ctx.upload(s)
+        except rt._abi.RtError as e:
+            if e.status != rt._abi.RT_ERR_UNSUPPORTED:
+                raise
+            print(f"seed {seed}: not expressible in the device layout ({str(e)[:90]})", flush=True)
+            continue
         rng = np.random.default_rng(seed)
         rays = np.zeros(a.rays, dtype=rt._abi.ray_dtype())
         rays["origin"] = rng.uniform(-14, 14, (a.rays, 3))
