@@ -214,6 +214,27 @@ def test_specialised_kernel_equals_generic_kernel_on_rare_ops(rt, ctx):
     assert dev[..., :3].mean() == pytest.approx(gen[..., :3].mean(), rel=2e-3)
 
 
+@pytest.mark.parametrize("idx", [0, 6, 7, 8])
+def test_layout_switches_render_the_same_image(rt, ctx, earth, idx):
+    """RT_LAYOUT_* (rt_b200.h): every way of flattening the same description traces the same keyed paths. Without hoisting the
+    media of cornell_smoke and final_scene stay in the op stream (class MEDIUM of the vote, medium_phase); without box
+    primitives every Quad::cube list is six quads again (class QUAD); without pruning every cull box of the reference's BVH
+    is tested."""
+    s, cam = small_scene(rt, idx, earth)
+    ds = ctx.upload(s)
+    want = ctx.render(ds, cam, 0, 4, seed=3)
+    ds.close()
+    for kw in ({"prune": False}, {"hoist_media": False}, {"box_primitives": False}, {"prune": False, "hoist_media": False, "box_primitives": False}):
+        dl = ctx.upload(s, rt.layout_flags(**kw))
+        got = ctx.render(dl, cam, 0, 4, seed=3)
+        dl.close()
+        assert np.all(got[..., 3] == 4)
+        # a cube as six quads takes its t from the quad's plane equation, the slab primitive from the corners: grazing hits may flip
+        floor = 0.985 if "box_primitives" in kw else 0.995
+        assert agreement(got, want[..., :3], 4) >= floor, kw
+        assert got[..., :3].mean() == pytest.approx(want[..., :3].mean(), rel=3e-3), kw
+
+
 def fuzz_camera(rt, seed, width=96, spp=4):
     """The camera tools/fuzz_render.py points at generated scene `seed` (same draws, so its log lines can be replayed)."""
     rng = np.random.default_rng(seed)
