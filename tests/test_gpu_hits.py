@@ -327,6 +327,47 @@ def test_hit_parity_one_million_rays(rt, ob, ctx, earth, idx):
     ds.close()
 
 
+def test_negative_radius_and_degenerate_primitives(rt, ob, ctx):
+    """Radii below zero (the book's hollow glass: `Sphere::new(c, -r, glass)`; the reference builds the box with min / max,
+    sphere.rs:24-31, and `(p - center) / radius` flips the normal), also moving, huge (f64 code) and as a medium boundary; a
+    flat `Quad::cube` (stays six quads) and a quad of 1e-6 units."""
+    rng = np.random.default_rng(3)
+    s = rt.Scene(bvh_seed=9)
+    glass = s.Dielectric(1.5)
+    white = s.Lambertian(s.SolidColor(0.7, 0.7, 0.7))
+    l = rt.HittableList()
+    for _ in range(12):
+        c = rng.uniform(-8, 8, 3)
+        l.add(s.Sphere(c, 1.5, glass))
+        l.add(s.Sphere(c, -1.2, glass))
+    for _ in range(6):
+        c = rng.uniform(-8, 8, 3)
+        l.add(s.Sphere(c, -0.8, white, target=c + rng.uniform(-1, 1, 3)))
+    l.add(s.Sphere((0, -1010, 0), -1000.0, white))
+    l.add(s.ConstantMedium(s.Sphere((3, 3, 3), -2.0, glass), 0.5, (1, 1, 1)))
+    l.add(s.cube((1, 1, 1), (2, 1, 3), white))
+    l.add(s.Quad((0, 0, 0), (1e-6, 0, 0), (0, 1e-6, 0), white))
+    s.finish(s.BVHNode(l))
+    ds = ctx.upload(s)
+    n = 1 << 15
+    rays = np.zeros(n, dtype=rt._abi.ray_dtype())
+    rays["origin"] = rng.uniform(-14, 14, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.5, 2, (n, 1))
+    rays["time"] = rng.random(n)
+    ref = ob.hit_batch(s.desc, rays, seed=5)
+    dev = ctx.hit_batch(ds, rays, seed=5)
+    assert int(ref["hit"].sum()) > 10000
+    check_hits(dev, ref, rays, max_inequivalent=6)
+    cam = rt.Camera(rt.CameraSettings(image_width=96, aspect_ratio=1.0, samples_per_pixel=4, max_depth=12, vfov=50.0, look_from=(0, 4, 26),
+                                      look_at=(0, 0, 0), background=(0.7, 0.8, 1.0)))
+    img = ctx.render(ds, cam, 0, 4, seed=2)
+    want, _ = ob.render(s.desc, cam, 0, 4, seed=2, mode=0)
+    close = np.abs(img[..., :3] - want[..., :3]) <= 1e-3 * np.maximum(1.0, np.abs(want[..., :3]))
+    assert close.all(axis=-1).mean() >= 0.985
+    ds.close()
+
+
 @pytest.mark.parametrize("seed", [2, 9, 11, 14, 24, 36])
 def test_hit_parity_rich_scenes(rt, ob, ctx, seed):
     """tools/fuzz_scenes.py::rich_scene: media inside instances, instances inside the boundary of an instanced medium, a
