@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+L=rust-tracing_b200/csrc
+rm -f gpurun_out/r2_ab16.log
+for s in 8 3 0 6; do timeout 400 python tools/ab_lib.py --scene $s --spp 400 --rounds 3 $L/librt_b200_base.so $L/librt_b200_nocoop.so $L/librt_b200.so 2>&1 | tail -4 >> gpurun_out/r2_ab16.log; done
+cat gpurun_out/r2_ab16.log
+timeout 300 python -m pytest tests/test_gpu_render.py -m gpu -q -x -k "pathwise or golden or noise or rich" 2>&1 | tail -3
