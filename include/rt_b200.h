@@ -333,6 +333,7 @@ int rt_jpeg_decode_nvjpeg(rt_context* ctx, const uint8_t* jpeg, size_t n_bytes, 
 #define RT_LAYOUT_NO_BOX_PRIMITIVES 2u  /* Quad::cube lists stay six quads */
 #define RT_LAYOUT_NO_HOIST 4u           /* media stay at their BVH position */
 #define RT_LAYOUT_OPS_IN_GLOBAL 8u      /* the render kernel reads the op stream from global memory, not from shared memory */
+#define RT_LAYOUT_GENERIC_KERNEL 16u    /* the render kernel's generic instantiation (every feature compiled in), not the one specialised on this scene */
 int rt_scene_upload_ex(rt_context* ctx, const rt_scene_desc* desc, uint32_t layout_flags, rt_scene** out);
 
 /* What rt_scene_upload would build for this description, computed on the host (no GPU needed): sizes of the device

@@ -25,7 +25,7 @@ RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT
  RT_HIT_CONSTANT_MEDIUM, RT_HIT_BVH) = range(7)
 RT_FLAG_MOVING = 1
 RT_FLAG_CUBE_LIST = 2
-RT_LAYOUT_NO_PRUNE, RT_LAYOUT_NO_BOX_PRIMITIVES, RT_LAYOUT_NO_HOIST, RT_LAYOUT_OPS_IN_GLOBAL = 1, 2, 4, 8
+RT_LAYOUT_NO_PRUNE, RT_LAYOUT_NO_BOX_PRIMITIVES, RT_LAYOUT_NO_HOIST, RT_LAYOUT_OPS_IN_GLOBAL, RT_LAYOUT_GENERIC_KERNEL = 1, 2, 4, 8, 16
 
 d3 = C.c_double * 3
 d6 = C.c_double * 6

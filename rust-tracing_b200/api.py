@@ -288,10 +288,11 @@ def builtin_scene(scene, image_width=0, samples_per_pixel=0, max_depth=0, scene_
     return s, settings
 
 
-def layout_flags(prune=True, box_primitives=True, hoist_media=True, ops_in_smem=True):
+def layout_flags(prune=True, box_primitives=True, hoist_media=True, ops_in_smem=True, generic_kernel=False):
     """RT_LAYOUT_* switches of the flattening (tests and A/B runs; the defaults are the product's layout)."""
     return ((0 if prune else A.RT_LAYOUT_NO_PRUNE) | (0 if box_primitives else A.RT_LAYOUT_NO_BOX_PRIMITIVES) |
-            (0 if hoist_media else A.RT_LAYOUT_NO_HOIST) | (0 if ops_in_smem else A.RT_LAYOUT_OPS_IN_GLOBAL))
+            (0 if hoist_media else A.RT_LAYOUT_NO_HOIST) | (0 if ops_in_smem else A.RT_LAYOUT_OPS_IN_GLOBAL) |
+            (A.RT_LAYOUT_GENERIC_KERNEL if generic_kernel else 0))
 
 
 def scene_layout(scene, flags=0):

@@ -261,17 +261,18 @@ static unsigned scene_features(const CompiledScene& cs) {
 
 typedef void (*render_fn)(const RenderParams);
 // The render kernel is specialised on what the scene holds (FEAT_*, rt_kernels.cuh): the instantiation that renders a scene
-// carries no code the scene cannot reach (the kernel is bound by instruction fetch: profiles/r2_k1_icache.md). The
-// instrumented build and the global-memory fallback exist in the generic form only.
-template <unsigned... F>
+// carries no code the scene cannot reach (the kernel is bound by instruction fetch: profiles/r2_k1_icache.md), for both
+// homes of the op stream (shared memory; global memory for a stream that does not fit). FEAT_ALL is the generic form
+// (RT_LAYOUT_GENERIC_KERNEL asks for it); the instrumented build exists in that form only.
+template <bool OPS_SMEM, unsigned... F>
 static render_fn mk_specialised(unsigned feat, std::integer_sequence<unsigned, F...>) {
-    static const render_fn table[] = {render_kernel_mk<false, true, F>...};
+    static const render_fn table[] = {render_kernel_mk<false, OPS_SMEM, F>...};
     return table[feat];
 }
 static render_fn mk_kernel(bool counting, bool ops_smem, unsigned feat) {
     if (counting) return ops_smem ? render_kernel_mk<true, true, FEAT_ALL> : render_kernel_mk<true, false, FEAT_ALL>;
-    if (!ops_smem) return render_kernel_mk<false, false, FEAT_ALL>;
-    return mk_specialised(feat & FEAT_ALL, std::make_integer_sequence<unsigned, FEAT_ALL + 1u>{});
+    if (!ops_smem) return mk_specialised<false>(feat & FEAT_ALL, std::make_integer_sequence<unsigned, FEAT_ALL + 1u>{});
+    return mk_specialised<true>(feat & FEAT_ALL, std::make_integer_sequence<unsigned, FEAT_ALL + 1u>{});
 }
 
 #ifdef RT_B200_DEV
@@ -324,6 +325,7 @@ struct rt_scene {
     CompiledScene compiled;
     uint32_t ops_bytes = 0;
     bool ops_in_global = false;
+    bool generic_kernel = false;     // RT_LAYOUT_GENERIC_KERNEL
     unsigned features = 0;       // FEAT_* the stream needs: picks the render kernel's instantiation
 };
 
@@ -656,6 +658,7 @@ int rt_scene_upload_ex(rt_context* c, const rt_scene_desc* desc, uint32_t layout
     c->live_scenes++;
     const char* err = nullptr;
     s->ops_in_global = (layout_flags & RT_LAYOUT_OPS_IN_GLOBAL) != 0;
+    s->generic_kernel = (layout_flags & RT_LAYOUT_GENERIC_KERNEL) != 0;
     int rc = compile_scene(desc, compile_options(c, layout_flags), &s->compiled, &err);
     if (rc < 0) { rt_scene_destroy(s); return fail(rc, err ? err : "compile_scene failed"); }
     const CompiledScene& cs = s->compiled;
@@ -844,7 +847,7 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
         if (lay.total > c->smem_optin) return fail(RT_ERR_INTERNAL, "render kernel: per-thread state does not fit in shared memory");
         prm.ops_bytes = in_smem ? s->ops_bytes : 0u;
         CU(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned int), stream));
-        render_fn fn = mk_kernel(counting, in_smem, s->features | (prm.cam.defocus ? FEAT_DEFOCUS : 0u));
+        render_fn fn = mk_kernel(counting, in_smem, s->generic_kernel ? FEAT_ALL : (s->features | (prm.cam.defocus ? FEAT_DEFOCUS : 0u)));
         fn<<<c->sm_count, kRenderThreads, lay.total, stream>>>(prm);
     }
     CU(cudaGetLastError());

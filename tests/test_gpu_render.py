@@ -177,24 +177,34 @@ def test_more_noise_textures_than_fit_in_shared_memory(rt, ob, ctx):
     ds.close()
 
 
+def render_variants(rt, ctx, s, cam, spp, seed):
+    """The same scene through the specialised instantiation (the product's pick) and through the generic one, with the op
+    stream in shared memory and in global memory."""
+    out = {}
+    for name, kw in (("specialised, shared", {}), ("generic, shared", {"generic_kernel": True}),
+                     ("specialised, global", {"ops_in_smem": False}), ("generic, global", {"ops_in_smem": False, "generic_kernel": True})):
+        ds = ctx.upload(s, rt.layout_flags(**kw))
+        out[name] = ctx.render(ds, cam, 0, spp, seed=seed)
+        ds.close()
+    return out
+
+
 @pytest.mark.parametrize("idx", range(9))
 def test_specialised_kernel_equals_generic_kernel(rt, ctx, earth, idx):
     """rt_scene_upload picks one of 32 render-kernel instantiations from the FEAT_* bits of the compiled stream (code the
-    scene cannot reach is compiled out); RT_LAYOUT_OPS_IN_GLOBAL runs the one generic instantiation (every feature in,
-    op stream read from global memory: the fall-back for streams that do not fit in shared memory). Both trace the same
-    keyed paths with the same arithmetic, so the images agree path by path; a feature bit the stream walk missed, or a
-    fall-back that reads the stream differently, would show here."""
+    scene cannot reach is compiled out), once for a stream staged in shared memory and once for a stream read from global
+    memory (RT_LAYOUT_OPS_IN_GLOBAL: what a stream too large for shared memory gets); RT_LAYOUT_GENERIC_KERNEL runs the
+    instantiation with every feature in. All four trace the same keyed paths with the same arithmetic, so the images agree
+    path by path; a feature bit the stream walk missed, or a fetch that reads the stream differently, would show here."""
     s, cam = small_scene(rt, idx, earth)
     spp = 4
-    ds = ctx.upload(s)
-    dev = ctx.render(ds, cam, 0, spp, seed=5)
-    ds.close()
-    dg = ctx.upload(s, rt.layout_flags(ops_in_smem=False))
-    gen = ctx.render(dg, cam, 0, spp, seed=5)
-    dg.close()
-    assert np.all(dev[..., 3] == spp) and np.all(gen[..., 3] == spp)
-    assert agreement(dev, gen[..., :3], spp) >= 0.995
-    assert dev[..., :3].mean() == pytest.approx(gen[..., :3].mean(), rel=2e-3)
+    img = render_variants(rt, ctx, s, cam, spp, 5)
+    dev = img.pop("specialised, shared")
+    assert np.all(dev[..., 3] == spp)
+    for name, other in img.items():
+        assert np.all(other[..., 3] == spp), name
+        assert agreement(dev, other[..., :3], spp) >= 0.995, name
+        assert dev[..., :3].mean() == pytest.approx(other[..., :3].mean(), rel=2e-3), name
 
 
 def test_specialised_kernel_equals_generic_kernel_on_rare_ops(rt, ctx):
@@ -204,14 +214,11 @@ def test_specialised_kernel_equals_generic_kernel_on_rare_ops(rt, ctx):
     s = nested_instances_scene(rt, np.random.default_rng(21))
     cam = rt.Camera(rt.CameraSettings(image_width=96, aspect_ratio=1.0, samples_per_pixel=4, max_depth=12, vfov=50.0,
                                       look_from=(0, 4, 22), look_at=(0, 0, 0), background=(0.7, 0.8, 1.0)))
-    ds = ctx.upload(s)
-    dev = ctx.render(ds, cam, 0, 4, seed=9)
-    ds.close()
-    dg = ctx.upload(s, rt.layout_flags(ops_in_smem=False))
-    gen = ctx.render(dg, cam, 0, 4, seed=9)
-    dg.close()
-    assert agreement(dev, gen[..., :3], 4) >= 0.995
-    assert dev[..., :3].mean() == pytest.approx(gen[..., :3].mean(), rel=2e-3)
+    img = render_variants(rt, ctx, s, cam, 4, 9)
+    dev = img.pop("specialised, shared")
+    for name, other in img.items():
+        assert agreement(dev, other[..., :3], 4) >= 0.995, name
+        assert dev[..., :3].mean() == pytest.approx(other[..., :3].mean(), rel=2e-3), name
 
 
 @pytest.mark.parametrize("idx", [0, 6, 7, 8])

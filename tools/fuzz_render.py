@@ -55,7 +55,7 @@ def main():
         ds = ctx.upload(s)
         dev = ctx.render(ds, cam, 0, a.spp, seed=seed)
         ds.close()
-        dg = ctx.upload(s, rt.layout_flags(ops_in_smem=False))
+        dg = ctx.upload(s, rt.layout_flags(ops_in_smem=False, generic_kernel=True))
         gen = ctx.render(dg, cam, 0, a.spp, seed=seed)
         dg.close()
         ref, _ = ob.render(s.desc, cam, 0, a.spp, seed=seed, mode=0)
