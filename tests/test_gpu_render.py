@@ -242,6 +242,41 @@ def test_layout_switches_render_the_same_image(rt, ctx, earth, idx):
         assert got[..., :3].mean() == pytest.approx(want[..., :3].mean(), rel=3e-3), kw
 
 
+def test_launches_on_two_streams_do_not_share_state(rt, ctx):
+    """rt_render_accumulate is asynchronous on the caller's stream. Every launch takes its own work counter and statistics
+    slot (a ring of 64 in the context), so launches in flight on different (non-blocking) streams neither hand out each
+    other's pools twice nor skip them: both framebuffers equal what the same calls give one after the other, and the
+    sample-count channel is exact."""
+    import torch
+    s, cam = small_scene(rt, 6, width=128)
+    s2, cam2 = small_scene(rt, 0, width=128)
+    ds, ds2 = ctx.upload(s), ctx.upload(s2)
+    (h, w), (h2, w2) = cam.shape, cam2.shape
+    want_a = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    want_b = torch.zeros((h2, w2, 4), dtype=torch.float32, device="cuda")
+    ctx.render_accumulate(ds, cam, 0, 64, 3, want_a.data_ptr())
+    ctx.render_accumulate(ds2, cam2, 8, 48, 4, want_b.data_ptr())
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        got_a = torch.zeros_like(want_a)
+        got_b = torch.zeros_like(want_b)
+        torch.cuda.synchronize()
+        # interleaved, nothing waits for anything: four launches in flight on two streams
+        ctx.render_accumulate(ds, cam, 0, 32, 3, got_a.data_ptr(), stream=sa.cuda_stream)
+        ctx.render_accumulate(ds2, cam2, 8, 24, 4, got_b.data_ptr(), stream=sb.cuda_stream)
+        ctx.render_accumulate(ds, cam, 32, 32, 3, got_a.data_ptr(), stream=sa.cuda_stream)
+        ctx.render_accumulate(ds2, cam2, 32, 24, 4, got_b.data_ptr(), stream=sb.cuda_stream)
+        rgb = ctx.finalize_rgb8(got_a.data_ptr(), h * w, 64.0, stream=sa.cuda_stream)    # ordered after the renders of its stream
+        torch.cuda.synchronize()
+        assert torch.all(got_a[..., 3] == 64) and torch.all(got_b[..., 3] == 48)
+        assert torch.allclose(got_a, want_a, rtol=2e-6, atol=1e-5) and torch.allclose(got_b, want_b, rtol=2e-6, atol=1e-5)
+        ref_rgb = ctx.finalize_rgb8(want_a.data_ptr(), h * w, 64.0)
+        assert (rgb == ref_rgb).mean() >= 0.9999
+    ds.close()
+    ds2.close()
+
+
 def fuzz_camera(rt, seed, width=96, spp=4):
     """The camera tools/fuzz_render.py points at generated scene `seed` (same draws, so its log lines can be replayed)."""
     rng = np.random.default_rng(seed)
