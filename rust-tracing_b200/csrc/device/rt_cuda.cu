@@ -185,6 +185,13 @@ __global__ void finalize_kernel(const float4* sum, int64_t n, float inv_spp, int
     }
 }
 
+// max_depth <= 0: ray_color returns black before it looks at the world (renderer.rs:140-142), so every sample adds
+// (0, 0, 0) and counts as one
+__global__ void black_samples_kernel(float4* sum, int64_t n, float count) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) sum[k].w += count;
+}
+
 __global__ void expand_image_kernel(const uint8_t* rgb8, int64_t n, const float* lut, float4* out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -797,6 +804,12 @@ static int launch_render(rt_context* c, const rt_scene* s, const rt_camera_desc*
     prm.seed = seed;
     prm.sample_begin = sample_begin;
     prm.sample_count = (int)sample_count;
+    if (cam->max_depth <= 0 && !counting) {
+        const int64_t n_pix = (int64_t)cam->image_width * cam->image_height;
+        black_samples_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, stream>>>(static_cast<float4*>(d_sum_rgba), n_pix, (float)sample_count);
+        CU(cudaGetLastError());
+        return RT_OK;
+    }
     prm.tiles_x = (prm.cam.width + kTileW - 1) / kTileW;
     prm.tiles_y = (prm.cam.height + kTileH - 1) / kTileH;
     // pool = tile x chunk samples; keep >= 64 pools per resident warp so the tail of the launch (warps running dry
@@ -866,8 +879,6 @@ static int check_render_args(rt_context* c, const rt_scene* s, const rt_camera_d
         return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": sample range must lie in [0, 2^32)");
     if (cam->image_width <= 0 || cam->image_height <= 0 || cam->image_width * cam->image_height > 0x7fffffff)
         return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": bad image size");
-    if (cam->max_depth <= 0)   // ray_color returns black at depth <= 0 (renderer.rs:140-142); the CLI scenes never ask for it
-        return fail(RT_ERR_INVALID_ARGUMENT, std::string(who) + ": max_depth must be positive");
     return RT_OK;
 }
 
@@ -887,6 +898,7 @@ int rt_render_count_ops(rt_context* c, const rt_scene* s, const rt_camera_desc* 
     int rc = check_render_args(c, s, cam, sample_begin, sample_count, counters, "rt_render_count_ops");
     if (rc < 0) return rc;
     if (capacity < (int)K_NUM) return fail(RT_ERR_OUT_OF_RANGE, "rt_render_count_ops: capacity too small");
+    if (cam->max_depth <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render_count_ops: nothing to count at max_depth <= 0");
     if (names_csv) *names_csv = kCounterNames;
     CU(cudaSetDevice(c->device));
     const size_t n = (size_t)cam->image_width * (size_t)cam->image_height;

@@ -126,6 +126,20 @@ def test_depth_exhaustion_and_lights_on_device(rt, ctx):
     ds2.close()
 
 
+@pytest.mark.parametrize("depth", [0, -3])
+def test_depth_zero_is_black_not_an_error(rt, ob, ctx, depth):
+    """ray_color returns black at depth <= 0 before it looks at the world (renderer.rs:140-142): every sample adds (0, 0, 0)
+    and counts."""
+    s, _ = small_scene(rt, 6, width=40)
+    cam = rt.Camera(rt.CameraSettings(image_width=40, aspect_ratio=1.0, samples_per_pixel=5, max_depth=depth, background=(0.7, 0.8, 1.0)))
+    ds = ctx.upload(s)
+    img = ctx.render(ds, cam, 0, 5)
+    ref, _ = ob.render(s.desc, cam, 0, 5, seed=0, mode=0)
+    assert ref.max() == 0.0
+    assert img[..., :3].max() == 0.0 and np.all(img[..., 3] == 5)
+    ds.close()
+
+
 def test_textures_against_golden(rt, ctx):
     g = np.load(os.path.join(GOLD, "textures.npz"))
     earth = rt.synthetic_earth(256, 128, seed=11)
