@@ -174,7 +174,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_t / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": f"synthetic scene (seeded layout); earth texels: {earth_src}",
-            "config": {"workload": "Book-2 final_scene 800x800 depth 40 (bounded sample: reduced spp)", "spp_per_step": spp},
+            # the same workload as the device arm names; what a step of THIS arm covers of it is the bounded sample
+            "config": {"workload": f"Book-2 final_scene {WORKLOAD['width']}x{WORKLOAD['height']}, {WORKLOAD['spp']} spp, depth {WORKLOAD['max_depth']} (BASELINE.json configs[4])",
+                       "sample": f"bounded: {spp} of the {WORKLOAD['spp']} spp per step (Mpaths/s does not depend on spp)", "spp_per_step": spp},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
