@@ -180,7 +180,7 @@ typedef struct rt_camera_desc {       /* Camera, camera.rs:38-51 */
     int64_t image_width;
     int64_t image_height;
     int32_t samples_per_pixel;
-    int32_t max_depth;
+    int32_t max_depth;                /* <= 0: every sample is black and counts, as ray_color returns (renderer.rs:140-142) */
     double background[3];
     double center[3];
     double pixel00_loc[3];
