@@ -205,6 +205,21 @@ def test_pruning_changes_no_hit_random_scenes(rt, seed):
     assert pruned.n_world <= full.n_world
 
 
+@pytest.mark.parametrize("seed", [0, 2, 6, 11, 14, 16, 24, 36])
+def test_layout_switches_change_no_hit_rich_scenes(rt, seed):
+    """rich_scene (media inside instances and instanced boundaries, reference boxes next to media, f64 spheres): the pruned
+    and the unpruned stream, and the stream with every medium left at its place in the tree, give the same closest hits
+    (bit-identical for pruning: boxes only cull; hoisting moves a medium's test, not its draw - the draw is keyed)."""
+    from fuzz_scenes import rich_scene
+    s = rich_scene(5000 + seed)
+    rays = random_rays(rt, np.random.default_rng(seed), 1 << 12)
+    a = opstream.hit_batch(opstream.Stream(rt.scene_ops(s)), rays, seed=seed)
+    b = opstream.hit_batch(opstream.Stream(rt.scene_ops(s, rt.layout_flags(prune=False))), rays, seed=seed)
+    c = opstream.hit_batch(opstream.Stream(rt.scene_ops(s, rt.layout_flags(hoist_media=False))), rays, seed=seed)
+    assert np.array_equal(a["hit"], b["hit"]) and np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["t"], b["t"])
+    assert np.array_equal(a["hit"], c["hit"]) and np.array_equal(a["prim_id"], c["prim_id"]) and np.array_equal(a["t"], c["t"])
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_stream_walk_deeply_nested_instances(rt, ob, seed):
     """Five levels of Translate / RotateY around lists and BVHs: the composed world -> local transforms and the parent
